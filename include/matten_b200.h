@@ -1,0 +1,230 @@
+/*
+ * matten_b200 -- C ABI of the B200-native (sm_100a) equivariant message-passing
+ * hot path of MatTen (wengroup/matten).
+ *
+ * Drop-in boundary.  The reference is pure Python; the arithmetic on this path
+ * lives in e3nn 0.5.1 / torch_scatter, called from src/matten/nn/*.py.  Every
+ * entry point below replaces one of those call sites (cited per function) and is
+ * what a `ctypes` / `torch.library` binding on the reference side binds (see
+ * INTEGRATION.md).  Conventions:
+ *
+ *   - plain device pointers + sizes; the caller owns every buffer (inputs,
+ *     outputs, workspaces) and allocates them with whatever allocator it uses
+ *     (torch in our host layer).  The library never allocates on the hot path
+ *     and never synchronises the stream;
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as
+ *     void*); any number of host threads may call concurrently;
+ *   - `dtype` selects the arithmetic type of every `void*` tensor of the call:
+ *     MT_F32 or MT_F64 (the reference's DTYPE, src/matten/data/_dtype.py:3);
+ *   - tensors are dense row-major; index tensors coming from the reference's
+ *     graph dict are int64 (src/matten/data/_dtype.py:4); bookkeeping produced
+ *     by this library (CSR row pointers, permutations) is int32;
+ *   - return value: MT_OK (0) or a negative mt_status; mt_last_error() returns a
+ *     thread-local message.  Nothing throws or exits across the boundary;
+ *   - data errors that can only be seen on the device (atomic number not in the
+ *     model's species list, unsorted batch vector, index out of range) are
+ *     OR-ed into a caller-provided int32 device flag word (`err_flag`, may be
+ *     NULL) so that no call has to synchronise; the caller reads it once per
+ *     batch (bits: MT_FLAG_*).
+ *   - there is NO CPU fallback: on a device that is not compute capability 10.x
+ *     every compute entry point returns MT_EARCH.
+ */
+#ifndef MATTEN_B200_H
+#define MATTEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MT_ABI_VERSION 1
+#define MT_MAX_MLP_LAYERS 6
+#define MT_LMAX 4
+
+typedef enum {
+  MT_OK = 0,
+  MT_EINVAL = -1, /* bad argument / unsupported configuration */
+  MT_EARCH = -2,  /* device is not sm_100 */
+  MT_ECUDA = -3   /* CUDA runtime error (message in mt_last_error) */
+} mt_status;
+
+typedef enum { MT_F32 = 0, MT_F64 = 1 } mt_dtype;
+
+/* activation ids (reference src/matten/nn/utils.py:14-26) */
+typedef enum {
+  MT_ACT_NONE = 0,
+  MT_ACT_SILU = 1,
+  MT_ACT_TANH = 2,
+  MT_ACT_SIGMOID = 3,
+  MT_ACT_SSP = 4, /* shifted softplus, src/matten/nn/_nequip.py:17-39 */
+  MT_ACT_ABS = 5
+} mt_act;
+
+/* bits of the device error flag word */
+#define MT_FLAG_BAD_SPECIES 1 /* atomic number outside the allowed list   */
+#define MT_FLAG_BAD_INDEX 2   /* edge / key index out of range            */
+#define MT_FLAG_UNSORTED 4    /* batch vector not non-decreasing          */
+
+typedef void* mt_stream; /* cudaStream_t */
+
+int mt_abi_version(void);
+const char* mt_last_error(void);
+/* MT_OK if `device` is compute capability 10.x, else MT_EARCH. */
+int mt_device_supported(int device);
+
+/* ------------------------------------------------------------------------- *
+ * Edge geometry.
+ * ------------------------------------------------------------------------- */
+
+/* a1: with_edge_vectors, reference src/matten/nn/_nequip.py:214-268.
+ *   vec[e] = pos[ei[1,e]] - pos[ei[0,e]] + shift[e] @ cell[batch[ei[0,e]]]
+ *   len[e] = |vec[e]|
+ * pos [N,3]; edge_index [2,E] int64; shift [E,3] and cell [B,3,3] may both be NULL
+ * (no periodic images); batch [N] int64 may be NULL when B == 1.
+ * edge_vec [E,3] and edge_len [E] are outputs (either may be NULL). */
+int mt_edge_vectors(int dtype, const void* pos, const int64_t* edge_index,
+                    const void* edge_cell_shift, const void* cell, const int64_t* batch,
+                    int64_t N, int64_t E, int64_t B, void* edge_vec, void* edge_len,
+                    int32_t* err_flag, mt_stream stream);
+
+/* a2: e3nn.o3.SphericalHarmonics(0..lmax, normalize=True, 'component'), reference
+ * src/matten/nn/_nequip.py:167-176.  edge_vec [E,3] -> edge_sh [E,(lmax+1)^2].
+ * normalize != 0 divides by the length first (the reference always does). */
+int mt_edge_sh(int dtype, const void* edge_vec, int64_t E, int lmax, int normalize,
+               void* edge_sh, mt_stream stream);
+
+/* a3 / a3': radial basis of the edge length, edge_len [E] -> edge_emb [E,num_basis].
+ *  mode 0: e3nn.math.soft_one_hot_linspace(x, start, end, n, 'bessel', cutoff) * sqrt(n)
+ *          (EdgeLengthEmbedding, reference src/matten/nn/embedding.py:185-203);
+ *  mode 1: BesselBasis(r_max=end) * PolynomialCutoff(r_max=end, p)  (RadialBasisEdge-
+ *          Encoding, reference src/matten/nn/_nequip.py:43-126,180-210); bessel_w [n]
+ *          holds the (trainable) frequencies, NULL means n*pi. */
+int mt_edge_radial(int dtype, const void* edge_len, int64_t E, int mode, int num_basis,
+                   double start, double end, int cutoff, double poly_p, const void* bessel_w,
+                   void* edge_emb, mt_stream stream);
+
+/* ------------------------------------------------------------------------- *
+ * Index bookkeeping (bit-exact integer work).
+ * ------------------------------------------------------------------------- */
+
+/* Stable counting sort of E int64 keys in [0, num_keys): the receiver-sorted CSR
+ * that replaces torch_scatter's atomics (reference src/matten/nn/conv.py:114), and
+ * the species grouping used by the species-indexed linears.
+ *   rowptr [num_keys+1]: rowptr[k] = #keys < k;  perm [E]: perm[i] = original index of
+ *   the i-th entry in sorted order (ties in ascending original index).
+ * perm may be NULL (row pointers only, e.g. graph pointers from the batch vector).
+ * workspace: mt_csr_workspace_bytes(num_keys, E) bytes. */
+size_t mt_csr_workspace_bytes(int64_t num_keys, int64_t E);
+int mt_csr_by_key(const int64_t* keys, int64_t E, int64_t num_keys, int32_t* rowptr,
+                  int32_t* perm, void* workspace, size_t workspace_bytes, int32_t* err_flag,
+                  mt_stream stream);
+
+/* out[i] = (int32) src[perm[i]]  (perm NULL: identity). */
+int mt_gather_i64_to_i32(const int64_t* src, const int32_t* perm, int64_t n, int32_t* out,
+                         mt_stream stream);
+
+/* Sets MT_FLAG_UNSORTED if keys is not non-decreasing. */
+int mt_check_sorted(const int64_t* keys, int64_t n, int32_t* err_flag, mt_stream stream);
+
+/* a4: _AtomicNumberToIndex + one-hot + Linear(S, dim, bias), reference
+ * src/matten/nn/embedding.py:85-110, 206-263.
+ *   idx = lut[Z - min_Z] (MT_FLAG_BAD_SPECIES if Z out of range or lut == -1)
+ *   node_attrs[n, :] = one_hot(idx, S);  node_feats[n, j] = lin_w[j, idx] + lin_b[j]
+ * atomic_numbers may be NULL when species_index (in/out, int64 [N]) is already given
+ * (z_given == 0). Any output may be NULL. lin_w is [dim, S] (torch Linear layout). */
+int mt_species_embed(int dtype, const int64_t* atomic_numbers, int z_given, const int64_t* lut,
+                     int64_t min_z, int64_t max_z, int num_species, int dim, const void* lin_w,
+                     const void* lin_b, int64_t N, int64_t* species_index, void* node_attrs,
+                     void* node_feats, int32_t* err_flag, mt_stream stream);
+
+/* ------------------------------------------------------------------------- *
+ * a6 + a7: fused  radial MLP -> uvu tensor product -> segmented sum over the
+ * receiver's edges -> / sqrt(#neighbours).  Replaces weight_nn + tp + scatter + div
+ * of reference src/matten/nn/conv.py:113-120 and src/matten/nn/utils.py:255-263.
+ * Per-edge weights and messages never touch HBM.
+ * ------------------------------------------------------------------------- */
+
+/* The "plan" is a set of small int32 device tables built by the host once per
+ * layer (matten_b200/plan.py: the uvu instruction list of reference
+ * src/matten/nn/utils.py:205-237 regrouped into warp work items by (l1,l2,l3)).
+ *   item_hdr  [num_items,2]  : {cg_type_id, cols_per_warp (power of two <= 32)}
+ *   slot_tab  [num_items,32,4]: per lane {weight column (-1 = idle lane), offset of
+ *                              x[u,:] in the x row, offset of the sh block, offset of
+ *                              out[u,:] in the output row}
+ * mlp: num_layers weight matrices, weights[i] is [sizes[i], sizes[i+1]] row-major (the
+ * e3nn FullyConnectedNet layout), applied as act(x @ W / sqrt(sizes[i])) * act_cst on
+ * all but the last layer; sizes[num_layers] == weight_numel of the tensor product. */
+typedef struct {
+  int32_t x_dim;        /* row length of x (node features)          */
+  int32_t y_dim;        /* row length of sh (edge attrs)            */
+  int32_t out_dim;      /* row length of the output (irreps_mid)    */
+  int32_t num_items;    /* warp work items                          */
+  const int32_t* item_hdr; /* device */
+  const int32_t* slot_tab; /* device */
+  int32_t mlp_num_layers;
+  int32_t mlp_sizes[MT_MAX_MLP_LAYERS + 1];
+  int32_t mlp_act;      /* mt_act of the hidden layers              */
+  double mlp_act_cst;   /* normalize2mom constant of that activation */
+} mt_conv_plan;
+
+/* x [N,x_dim]; sh [E,y_dim], emb [E,mlp_sizes[0]] in ORIGINAL edge order;
+ * rowptr [N+1], perm [E], src_sorted [E] from mt_csr_by_key / mt_gather_i64_to_i32 on
+ * edge_index[1] / edge_index[0].  out [N,out_dim] =
+ *   (sum_{e: dst(e)=n} msg_e) / sqrt(avg_num_neighbors)        if num_neigh == NULL
+ *   (sum ...)             / sqrt(num_neigh[n])                  otherwise (reference
+ *   src/matten/nn/conv.py:116-120). Summation order is the CSR order: deterministic. */
+int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* sh,
+                const void* emb, const void* const* mlp_weights, const int32_t* rowptr,
+                const int32_t* perm, const int32_t* src_sorted, double avg_num_neighbors,
+                const void* num_neigh, void* out, int64_t N, int64_t E, mt_stream stream);
+
+/* ------------------------------------------------------------------------- *
+ * a8 / a11 / a13 / a14: irreps-wise linear maps.
+ *   FullyConnectedTensorProduct(x, one_hot(species), out)  (reference
+ *   src/matten/nn/conv.py:59-61,77-79,84-86)  ==  species-indexed linear;
+ *   e3nn.o3.Linear (reference src/matten/nn/nodewise.py:111,
+ *   model_factory/tfn_scalar_tensor.py:50) is the num_species == 1 case, and
+ *   CartesianTensor.to_cartesian (reference src/matten/utils.py:123-124) is a single
+ *   dense block.
+ * For each block b:  out[n, out_off + w*dim + m] (+)= scale *
+ *        sum_u weight[w_off + (u*S + s_n)*mul_out + w] * x[n, in_off + u*dim + m]
+ * A block with mul_in == 0 zero-fills its output range (irreps with no path).
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t in_off, out_off, mul_in, mul_out, dim, w_off;
+  double scale;
+} mt_lin_block;
+
+/* species_perm [N] / species_ptr [S+1]: nodes grouped by species (mt_csr_by_key on
+ * species_index); both NULL when num_species == 1.  accumulate != 0 adds into out. */
+int mt_linear_fwd(int dtype, const mt_lin_block* blocks, int num_blocks, int in_dim,
+                  int out_dim, int num_species, const void* x, const void* weight,
+                  const int32_t* species_perm, const int32_t* species_ptr, int accumulate,
+                  void* out, int64_t N, mt_stream stream);
+
+/* ------------------------------------------------------------------------- *
+ * a9 + a10: e3nn.nn.Gate followed by e3nn.nn.BatchNorm in eval mode (reference
+ * src/matten/nn/utils.py:134-140, 418, applied at src/matten/nn/conv.py:209-211).
+ * Per OUTPUT element j (tables are device arrays of length out_dim):
+ *   v = x[n, src_idx[j]]
+ *   gate_idx[j] <  0 : y = act_id[j](v) * act_cst[j]                 (scalar)
+ *   gate_idx[j] >= 0 : y = v * act_id[j](x[n, gate_idx[j]]) * act_cst[j]  (gated)
+ *   out[n,j] = y * affine_a[j] + affine_b[j]      (affine_* NULL: identity)
+ * ------------------------------------------------------------------------- */
+int mt_gate_fwd(int dtype, const void* x, int in_dim, int out_dim, const int32_t* src_idx,
+                const int32_t* gate_idx, const int32_t* act_id, const void* act_cst,
+                const void* affine_a, const void* affine_b, void* out, int64_t N,
+                mt_stream stream);
+
+/* a12: torch_scatter.scatter(x, batch, reduce) over a SORTED batch vector (reference
+ * src/matten/nn/nodewise.py:142-148).  ptr [B+1] from mt_csr_by_key on batch.
+ * mode: 0 sum, 1 mean, 2 min, 3 max.  x [N,dim] -> out [B,dim]. */
+int mt_segment_reduce(int dtype, const void* x, const int32_t* ptr, int dim, int64_t B,
+                      int mode, void* out, mt_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATTEN_B200_H */

@@ -1,0 +1,124 @@
+// Shared helpers for the matten_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/matten_b200.h"
+
+namespace mt {
+
+// ----------------------------------------------------------------- errors --
+char* last_error_buf();  // thread-local, defined in api.cu
+int set_error(int code, const char* fmt, ...);
+int check_device();  // MT_OK iff current device is cc 10.x
+
+#define MT_CUDA_OK(expr)                                                              \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess)                                                            \
+      return ::mt::set_error(MT_ECUDA, "%s failed: %s (%s:%d)", #expr,                \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);             \
+  } while (0)
+
+#define MT_LAUNCH_OK()                                                                \
+  do {                                                                                \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess)                                                            \
+      return ::mt::set_error(MT_ECUDA, "kernel launch failed: %s (%s:%d)",            \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);             \
+  } while (0)
+
+#define MT_REQUIRE(cond, ...)                                                         \
+  do {                                                                                \
+    if (!(cond)) return ::mt::set_error(MT_EINVAL, __VA_ARGS__);                      \
+  } while (0)
+
+#define MT_ENTRY_GUARD()                                                              \
+  do {                                                                                \
+    int _rc = ::mt::check_device();                                                   \
+    if (_rc != MT_OK) return _rc;                                                     \
+  } while (0)
+
+// dispatch on dtype: calls FN<float>(...) or FN<double>(...)
+#define MT_DISPATCH_DTYPE(dtype, ...)                                                 \
+  do {                                                                                \
+    if ((dtype) == MT_F32) {                                                          \
+      using T = float;                                                                \
+      __VA_ARGS__                                                                     \
+    } else if ((dtype) == MT_F64) {                                                   \
+      using T = double;                                                               \
+      __VA_ARGS__                                                                     \
+    } else {                                                                          \
+      return ::mt::set_error(MT_EINVAL, "unknown dtype %d", (int)(dtype));            \
+    }                                                                                 \
+  } while (0)
+
+inline cudaStream_t as_stream(mt_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;  // B200
+
+template <typename I>
+__host__ __device__ constexpr I ceil_div(I a, I b) {
+  return (a + b - 1) / b;
+}
+
+__host__ __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+// ------------------------------------------------------------ activations --
+template <typename T>
+__device__ __forceinline__ T act_sigmoid(T v) {
+  return T(1) / (T(1) + exp(-v));
+}
+template <>
+__device__ __forceinline__ float act_sigmoid<float>(float v) {
+  return 1.0f / (1.0f + expf(-v));
+}
+
+template <typename T>
+__device__ __forceinline__ T act_softplus(T v) {  // torch.nn.Softplus(beta=1, threshold=20)
+  return v > T(20) ? v : log1p(exp(v));
+}
+
+template <typename T>
+__device__ __forceinline__ T act_tanh(T v) {
+  return tanh(v);
+}
+
+// value of activation `id` (un-normalised)
+template <typename T>
+__device__ __forceinline__ T apply_act(int id, T v) {
+  switch (id) {
+    case MT_ACT_SILU: return v * act_sigmoid(v);
+    case MT_ACT_TANH: return act_tanh(v);
+    case MT_ACT_SIGMOID: return act_sigmoid(v);
+    case MT_ACT_SSP: return act_softplus(v) - T(0.6931471805599453);
+    case MT_ACT_ABS: return fabs(v);
+    default: return v;
+  }
+}
+
+// derivative of activation `id`
+template <typename T>
+__device__ __forceinline__ T apply_act_grad(int id, T v) {
+  switch (id) {
+    case MT_ACT_SILU: {
+      T s = act_sigmoid(v);
+      return s * (T(1) + v * (T(1) - s));
+    }
+    case MT_ACT_TANH: {
+      T t = act_tanh(v);
+      return T(1) - t * t;
+    }
+    case MT_ACT_SIGMOID: {
+      T s = act_sigmoid(v);
+      return s * (T(1) - s);
+    }
+    case MT_ACT_SSP: return v > T(20) ? T(1) : act_sigmoid(v);
+    case MT_ACT_ABS: return v > T(0) ? T(1) : (v < T(0) ? T(-1) : T(0));
+    default: return T(1);
+  }
+}
+
+}  // namespace mt

@@ -1,0 +1,136 @@
+// Host side of the fused convolution entry points (include/matten_b200.h: mt_conv_fwd).
+#include <stdlib.h>
+
+#include "conv_fwd.cuh"
+
+namespace mt {
+
+template <typename T, int HP>
+int launch_conv_fwd(const ConvFwdParams& p, int grid, int threads, size_t smem, cudaStream_t st);
+
+#define MT_DECL(T, HP) \
+  template <> int launch_conv_fwd<T, HP>(const ConvFwdParams&, int, int, size_t, cudaStream_t);
+MT_DECL(float, 8) MT_DECL(float, 16) MT_DECL(float, 32) MT_DECL(float, 64)
+MT_DECL(double, 8) MT_DECL(double, 16) MT_DECL(double, 32) MT_DECL(double, 64)
+#undef MT_DECL
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+static int pad_hp(int h) {
+  if (h <= 8) return 8;
+  if (h <= 16) return 16;
+  if (h <= 32) return 32;
+  if (h <= 64) return 64;
+  return -1;
+}
+
+static int validate_plan(const mt_conv_plan* plan) {
+  MT_REQUIRE(plan != nullptr, "null plan");
+  MT_REQUIRE(plan->x_dim > 0 && plan->y_dim > 0 && plan->out_dim > 0 && plan->num_items > 0, "bad plan dims");
+  MT_REQUIRE(plan->item_hdr && plan->slot_tab, "plan tables missing");
+  MT_REQUIRE(plan->mlp_num_layers >= 1 && plan->mlp_num_layers <= MT_MAX_MLP_LAYERS,
+             "mlp_num_layers %d not in 1..%d", plan->mlp_num_layers, MT_MAX_MLP_LAYERS);
+  for (int i = 0; i <= plan->mlp_num_layers; ++i) MT_REQUIRE(plan->mlp_sizes[i] > 0, "bad mlp size");
+  MT_REQUIRE(pad_hp(plan->mlp_sizes[plan->mlp_num_layers - 1]) > 0,
+             "last hidden size %d > 64 not supported", plan->mlp_sizes[plan->mlp_num_layers - 1]);
+  for (int i = 0; i < plan->mlp_num_layers; ++i)
+    MT_REQUIRE(plan->mlp_sizes[i] <= 256, "mlp layer size %d > 256 not supported", plan->mlp_sizes[i]);
+  return MT_OK;
+}
+
+template <typename T>
+static int conv_fwd_impl(const mt_conv_plan* plan, const void* x, const void* sh, const void* emb,
+                         const void* const* mlp_weights, const int32_t* rowptr, const int32_t* perm,
+                         const int32_t* src_sorted, double avg, const void* num_neigh, void* out, int64_t N,
+                         int64_t E, cudaStream_t st) {
+  ConvFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.x_dim = plan->x_dim;
+  p.y_dim = plan->y_dim;
+  p.out_dim = plan->out_dim;
+  p.num_items = plan->num_items;
+  p.item_hdr = plan->item_hdr;
+  p.slot_tab = plan->slot_tab;
+  p.nl = plan->mlp_num_layers;
+  int hp_max = 8;
+  for (int i = 0; i <= p.nl; ++i) p.sizes[i] = plan->mlp_sizes[i];
+  for (int i = 0; i < p.nl; ++i) {
+    p.w[i] = mlp_weights[i];
+    int h8 = (plan->mlp_sizes[i] + 7) / 8 * 8;
+    if (h8 > hp_max) hp_max = h8;
+  }
+  const int HP = pad_hp(p.sizes[p.nl - 1]);
+  if (HP > hp_max) hp_max = HP;
+  p.hp_max = hp_max;
+  p.act = plan->mlp_act;
+  p.act_cst = plan->mlp_act_cst;
+  p.x = x; p.sh = sh; p.emb = emb;
+  p.rowptr = rowptr; p.perm = perm; p.src = src_sorted;
+  p.avg = avg; p.num_neigh = num_neigh; p.out = out;
+  p.N = N; p.E = E;
+  p.xs_stride = p.x_dim | 1;
+
+  // chunk size from the shared-memory budget
+  const size_t per_edge = (size_t)(2 * hp_max + p.xs_stride + p.y_dim) * sizeof(T);
+  size_t budget = (size_t)env_int("MT_CONV_SMEM_KB", sizeof(T) == 4 ? 72 : 100) * 1024;
+  int EC = (int)(budget / per_edge);
+  EC = EC / 8 * 8;
+  if (EC > 256) EC = 256;
+  if (EC < 8) EC = 8;
+  EC = env_int("MT_CONV_EC", EC);
+  p.chunk_edges = EC;
+  double avg_deg = N > 0 ? (double)E / (double)N : 1.0;
+  int TN = (int)((double)EC / (avg_deg > 1.0 ? avg_deg : 1.0));
+  if (TN < 1) TN = 1;
+  if (TN > 32) TN = 32;
+  p.tile_nodes = env_int("MT_CONV_TN", TN);
+  const size_t smem = (size_t)EC * per_edge;
+  MT_REQUIRE(smem <= 227 * 1024, "conv tile needs %zu bytes of shared memory", smem);
+  const int threads = env_int("MT_CONV_THREADS", 256);
+  MT_REQUIRE(threads >= 32 && threads <= 256 && threads % 32 == 0, "MT_CONV_THREADS must be 32..256");
+  int64_t tiles = ceil_div<int64_t>(N, p.tile_nodes);
+  int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 8) ctas_per_sm = 8;
+  int64_t grid = (int64_t)kNumSMs * ctas_per_sm;
+  if (grid > tiles) grid = tiles;
+  if (grid < 1) grid = 1;
+  switch (HP) {
+    case 8: return launch_conv_fwd<T, 8>(p, (int)grid, threads, smem, st);
+    case 16: return launch_conv_fwd<T, 16>(p, (int)grid, threads, smem, st);
+    case 32: return launch_conv_fwd<T, 32>(p, (int)grid, threads, smem, st);
+    case 64: return launch_conv_fwd<T, 64>(p, (int)grid, threads, smem, st);
+  }
+  return set_error(MT_EINVAL, "unsupported hidden size");
+}
+
+}  // namespace mt
+
+using namespace mt;
+
+extern "C" {
+
+int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* sh, const void* emb,
+                const void* const* mlp_weights, const int32_t* rowptr, const int32_t* perm,
+                const int32_t* src_sorted, double avg_num_neighbors, const void* num_neigh, void* out,
+                int64_t N, int64_t E, mt_stream stream) {
+  MT_ENTRY_GUARD();
+  int rc = validate_plan(plan);
+  if (rc != MT_OK) return rc;
+  MT_REQUIRE(N >= 0 && E >= 0, "negative size");
+  if (N == 0) return MT_OK;
+  MT_REQUIRE(x && out && rowptr && mlp_weights, "null pointer");
+  MT_REQUIRE(E == 0 || (sh && emb && perm && src_sorted), "null edge pointer");
+  MT_REQUIRE(num_neigh != nullptr || avg_num_neighbors > 0.0, "avg_num_neighbors must be > 0");
+  for (int i = 0; i < plan->mlp_num_layers; ++i) MT_REQUIRE(mlp_weights[i] != nullptr, "null MLP weight %d", i);
+  MT_DISPATCH_DTYPE(dtype, {
+    return conv_fwd_impl<T>(plan, x, sh, emb, mlp_weights, rowptr, perm, src_sorted, avg_num_neighbors,
+                            num_neigh, out, N, E, as_stream(stream));
+  });
+  return MT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,294 @@
+// Node-side kernels: species-indexed irreps linear (a8/a11/a13/a14), Gate + BatchNorm
+// affine (a9/a10), segmented pooling (a12).  See include/matten_b200.h for the contract.
+#include "common.cuh"
+
+namespace mt {
+
+// =========================================================================
+// irreps-wise (species-indexed) linear
+//   reference: e3nn FullyConnectedTensorProduct(x, one_hot, out) at
+//   src/matten/nn/conv.py:59-61,77-79,84-86 and e3nn.o3.Linear at
+//   src/matten/nn/nodewise.py:111.  With one-hot attributes the "uvw" tensor product is
+//   a per-species dense matrix per irrep type; nodes are grouped by species so each CTA
+//   multiplies a [rows x mul_in] tile (rows = (node, m)) by ONE [mul_in x mul_out]
+//   weight slice staged in shared memory (register-tiled 4x4 FMA micro-kernel).
+// =========================================================================
+constexpr int kLinMaxBlocks = 24;
+constexpr int kLinRows = 64;  // (node, m) rows per CTA
+constexpr int kLinCols = 64;  // output channels per CTA
+constexpr int kLinK = 32;     // u-chunk
+
+struct LinParams {
+  int num_blocks;
+  int32_t in_off[kLinMaxBlocks], out_off[kLinMaxBlocks], mul_in[kLinMaxBlocks], mul_out[kLinMaxBlocks],
+      dim[kLinMaxBlocks], w_off[kLinMaxBlocks];
+  double scale[kLinMaxBlocks];
+  int32_t cta_begin[kLinMaxBlocks + 1];  // prefix of CTA counts per block
+  int32_t col_chunks[kLinMaxBlocks];     // ceil(mul_out / kLinCols)
+  int32_t nodes_per_tile[kLinMaxBlocks];
+  int in_dim, out_dim, S;
+  const void* x;
+  const void* weight;
+  const int32_t* sperm;
+  const int32_t* sptr;
+  int accumulate;
+  void* out;
+  int64_t N;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
+  // staging buffers; the output tile aliases them after the last k-chunk
+  constexpr int kStageElems = kLinK * (kLinRows + 4) + kLinK * kLinCols;
+  static_assert(kStageElems >= kLinRows * (kLinCols + 1), "output tile must fit in the staging buffers");
+  __shared__ __align__(16) unsigned char lin_smem[sizeof(T) * kStageElems];
+  T(*xsT)[kLinRows + 4] = reinterpret_cast<T(*)[kLinRows + 4]>(lin_smem);
+  T(*ws)[kLinCols] = reinterpret_cast<T(*)[kLinCols]>(lin_smem + sizeof(T) * kLinK * (kLinRows + 4));
+  T(*ot)[kLinCols + 1] = reinterpret_cast<T(*)[kLinCols + 1]>(lin_smem);
+  __shared__ int s_nodes[kLinRows];
+
+  // which block / node tile / column chunk am I?
+  int b = 0;
+  while (b + 1 < p.num_blocks && (int)blockIdx.x >= p.cta_begin[b + 1]) ++b;
+  int local = blockIdx.x - p.cta_begin[b];
+  const int cc = local % p.col_chunks[b];
+  int tile = local / p.col_chunks[b];
+  const int TN = p.nodes_per_tile[b];
+  const int mi = p.mul_in[b], mo = p.mul_out[b], d = p.dim[b];
+  // locate (species, tile-in-species)
+  int s = 0;
+  int64_t begin = 0, end = 0;
+  if (p.S == 1 && p.sptr == nullptr) {
+    begin = (int64_t)tile * TN;
+    end = imin64(begin + TN, p.N);
+    if (begin >= p.N) return;
+  } else {
+    bool found = false;
+    for (s = 0; s < p.S; ++s) {
+      int cnt = p.sptr[s + 1] - p.sptr[s];
+      int nt = (cnt + TN - 1) / TN;
+      if (tile < nt) {
+        begin = p.sptr[s] + (int64_t)tile * TN;
+        end = imin64(begin + TN, (int64_t)p.sptr[s + 1]);
+        found = true;
+        break;
+      }
+      tile -= nt;
+    }
+    if (!found) return;
+  }
+  const int tn = (int)(end - begin);
+  const int tid = threadIdx.x;
+  if (tid < tn) s_nodes[tid] = p.sperm ? p.sperm[begin + tid] : (int)(begin + tid);
+  __syncthreads();
+
+  const T* __restrict__ X = static_cast<const T*>(p.x);
+  const T* __restrict__ W = static_cast<const T*>(p.weight);
+  T* __restrict__ OUT = static_cast<T*>(p.out);
+  const int c0 = cc * kLinCols;
+  const int ncols = min(kLinCols, mo - c0);
+  const int R = tn * d;
+
+  if (mi == 0) {  // irreps with no incoming path: zeros
+    if (!p.accumulate) {
+      for (int t = tid; t < tn * ncols * d; t += blockDim.x) {
+        int j = t / (ncols * d), q = t - j * (ncols * d);
+        OUT[(size_t)s_nodes[j] * p.out_dim + p.out_off[b] + c0 * d + q] = T(0);
+      }
+    }
+    return;
+  }
+
+  const int tc = tid & 15, tr = tid >> 4;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+
+  for (int u0 = 0; u0 < mi; u0 += kLinK) {
+    const int ku = min(kLinK, mi - u0);
+    // stage weights  ws[uu][c] = W[w_off + ((u0+uu)*S + s)*mo + c0 + c]
+    for (int t = tid; t < kLinK * kLinCols; t += blockDim.x) {
+      int uu = t / kLinCols, c = t - uu * kLinCols;
+      T v = T(0);
+      if (uu < ku && c < ncols) v = W[(size_t)p.w_off[b] + ((size_t)(u0 + uu) * p.S + s) * mo + c0 + c];
+      ws[uu][c] = v;
+    }
+    // stage x transposed  xsT[uu][j*d+m] = X[node_j, in_off + (u0+uu)*d + m]
+    for (int t = tid; t < kLinRows * kLinK; t += blockDim.x) (&xsT[0][0])[(t / kLinRows) * (kLinRows + 4) + (t % kLinRows)] = T(0);
+    __syncthreads();
+    const int seg = ku * d;
+    for (int t = tid; t < tn * seg; t += blockDim.x) {
+      int j = t / seg, q = t - j * seg;
+      int uu = q / d, m = q - uu * d;
+      xsT[uu][j * d + m] = X[(size_t)s_nodes[j] * p.in_dim + p.in_off[b] + u0 * d + q];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int uu = 0; uu < kLinK; ++uu) {
+      T a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = xsT[uu][tr * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = ws[uu][tc * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const T scale = T(p.scale[b]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ot[tr * 4 + i][tc * 4 + j] = acc[i][j] * scale;
+  __syncthreads();
+  // coalesced write: per node the (w, m) range is contiguous
+  const int span = ncols * d;
+  for (int t = tid; t < tn * span; t += blockDim.x) {
+    int j = t / span, q = t - j * span;
+    int w = q / d, m = q - w * d;
+    size_t o = (size_t)s_nodes[j] * p.out_dim + p.out_off[b] + c0 * d + q;
+    T v = ot[j * d + m][w];
+    OUT[o] = p.accumulate ? (OUT[o] + v) : v;
+  }
+  (void)R;
+}
+
+// =========================================================================
+// Gate (+ folded BatchNorm affine)      reference src/matten/nn/utils.py:134-140,418
+// =========================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) gate_fwd_kernel(const T* __restrict__ x, int in_dim, int out_dim,
+                                                       const int32_t* __restrict__ src_idx,
+                                                       const int32_t* __restrict__ gate_idx,
+                                                       const int32_t* __restrict__ act_id,
+                                                       const T* __restrict__ act_cst,
+                                                       const T* __restrict__ aff_a,
+                                                       const T* __restrict__ aff_b, T* __restrict__ out,
+                                                       int64_t N) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= N * out_dim) return;
+  int64_t n = t / out_dim;
+  int j = (int)(t - n * out_dim);
+  const T* xr = x + n * in_dim;
+  T v = xr[src_idx[j]];
+  int g = gate_idx[j];
+  T y;
+  if (g < 0) y = apply_act<T>(act_id[j], v) * act_cst[j];
+  else y = v * (apply_act<T>(act_id[j], xr[g]) * act_cst[j]);
+  if (aff_a) y = y * aff_a[j] + aff_b[j];
+  out[t] = y;
+}
+
+// =========================================================================
+// segmented pooling                     reference src/matten/nn/nodewise.py:142-148
+// =========================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) segment_reduce_kernel(const T* __restrict__ x,
+                                                             const int32_t* __restrict__ ptr, int dim,
+                                                             int64_t B, int mode, T* __restrict__ out) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= B * dim) return;
+  int64_t b = t / dim;
+  int j = (int)(t - b * dim);
+  int n0 = ptr[b], n1 = ptr[b + 1];
+  T acc = T(0);
+  if (n1 > n0) {
+    acc = x[(size_t)n0 * dim + j];
+    for (int n = n0 + 1; n < n1; ++n) {
+      T v = x[(size_t)n * dim + j];
+      if (mode <= 1) acc += v;
+      else if (mode == 2) acc = v < acc ? v : acc;
+      else acc = v > acc ? v : acc;
+    }
+    if (mode == 1) acc = acc / T(n1 - n0);
+  }
+  out[t] = acc;
+}
+
+}  // namespace mt
+
+using namespace mt;
+
+extern "C" {
+
+int mt_linear_fwd(int dtype, const mt_lin_block* blocks, int num_blocks, int in_dim, int out_dim,
+                  int num_species, const void* x, const void* weight, const int32_t* species_perm,
+                  const int32_t* species_ptr, int accumulate, void* out, int64_t N, mt_stream stream) {
+  MT_ENTRY_GUARD();
+  MT_REQUIRE(blocks && num_blocks > 0 && num_blocks <= kLinMaxBlocks, "num_blocks %d not in 1..%d", num_blocks,
+             kLinMaxBlocks);
+  MT_REQUIRE(in_dim > 0 && out_dim > 0 && num_species >= 1, "bad dims");
+  MT_REQUIRE((species_perm == nullptr) == (species_ptr == nullptr), "species_perm/ptr must be given together");
+  MT_REQUIRE(num_species == 1 || species_ptr != nullptr, "species grouping required when num_species > 1");
+  if (N == 0) return MT_OK;
+  MT_REQUIRE(x && out, "null pointer");
+  LinParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_blocks = num_blocks;
+  int64_t total = 0;
+  for (int b = 0; b < num_blocks; ++b) {
+    const mt_lin_block& k = blocks[b];
+    MT_REQUIRE(k.dim >= 1 && k.dim <= kLinRows && k.mul_out > 0 && k.mul_in >= 0, "bad linear block %d", b);
+    MT_REQUIRE(k.out_off >= 0 && k.out_off + k.mul_out * k.dim <= out_dim, "block %d exceeds out_dim", b);
+    MT_REQUIRE(k.mul_in == 0 || (k.in_off >= 0 && k.in_off + k.mul_in * k.dim <= in_dim), "block %d exceeds in_dim", b);
+    MT_REQUIRE(k.mul_in == 0 || weight != nullptr, "null weight");
+    p.in_off[b] = k.in_off; p.out_off[b] = k.out_off; p.mul_in[b] = k.mul_in; p.mul_out[b] = k.mul_out;
+    p.dim[b] = k.dim; p.w_off[b] = k.w_off; p.scale[b] = k.scale;
+    int tn = kLinRows / k.dim;
+    if (tn < 1) tn = 1;
+    p.nodes_per_tile[b] = tn;
+    p.col_chunks[b] = ceil_div<int>(k.mul_out, kLinCols);
+    int64_t tiles = ceil_div<int64_t>(N, tn) + (species_ptr ? num_species : 0);
+    p.cta_begin[b] = (int32_t)total;
+    total += tiles * p.col_chunks[b];
+    MT_REQUIRE(total < (int64_t)2147483647, "grid too large");
+  }
+  p.cta_begin[num_blocks] = (int32_t)total;
+  p.in_dim = in_dim; p.out_dim = out_dim; p.S = num_species;
+  p.x = x; p.weight = weight; p.sperm = species_perm; p.sptr = species_ptr;
+  p.accumulate = accumulate; p.out = out; p.N = N;
+  MT_DISPATCH_DTYPE(dtype, {
+    linear_fwd_kernel<T><<<(unsigned)total, 256, 0, as_stream(stream)>>>(p);
+  });
+  MT_LAUNCH_OK();
+  return MT_OK;
+}
+
+int mt_gate_fwd(int dtype, const void* x, int in_dim, int out_dim, const int32_t* src_idx,
+                const int32_t* gate_idx, const int32_t* act_id, const void* act_cst, const void* affine_a,
+                const void* affine_b, void* out, int64_t N, mt_stream stream) {
+  MT_ENTRY_GUARD();
+  MT_REQUIRE(in_dim > 0 && out_dim > 0, "bad dims");
+  MT_REQUIRE((affine_a == nullptr) == (affine_b == nullptr), "affine_a/b must be given together");
+  if (N == 0) return MT_OK;
+  MT_REQUIRE(x && out && src_idx && gate_idx && act_id && act_cst, "null pointer");
+  int64_t total = N * out_dim;
+  MT_DISPATCH_DTYPE(dtype, {
+    gate_fwd_kernel<T><<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(
+        (const T*)x, in_dim, out_dim, src_idx, gate_idx, act_id, (const T*)act_cst, (const T*)affine_a,
+        (const T*)affine_b, (T*)out, N);
+  });
+  MT_LAUNCH_OK();
+  return MT_OK;
+}
+
+int mt_segment_reduce(int dtype, const void* x, const int32_t* ptr, int dim, int64_t B, int mode, void* out,
+                      mt_stream stream) {
+  MT_ENTRY_GUARD();
+  MT_REQUIRE(dim > 0 && mode >= 0 && mode <= 3, "bad arguments");
+  if (B == 0) return MT_OK;
+  MT_REQUIRE(x && ptr && out, "null pointer");
+  int64_t total = B * dim;
+  MT_DISPATCH_DTYPE(dtype, {
+    segment_reduce_kernel<T><<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(
+        (const T*)x, ptr, dim, B, mode, (T*)out);
+  });
+  MT_LAUNCH_OK();
+  return MT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,294 @@
+"""
+Thin functional layer over the C ABI (include/matten_b200.h): torch tensors in, torch
+tensors out.  torch is used for device memory and the current CUDA stream only; every
+computation below is a hand-written sm_100a kernel in libmatten_b200.so.
+
+No CPU path exists: CPU tensors raise, and on a GPU that is not sm_100 the library
+returns MT_EARCH which is raised as RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvPlanStruct, LinBlockStruct, MT_F32, MT_F64, check
+
+#: number of kernel launches issued through this module (bench.py reports it)
+LAUNCHES = 0
+
+
+def _bump(n: int = 1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return MT_F32
+    if t.dtype == torch.float64:
+        return MT_F64
+    raise TypeError(f"matten_b200 computes in float32 or float64, got {t.dtype}")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _req(t: torch.Tensor, name: str, dtype=None):
+    if not t.is_cuda:
+        raise RuntimeError(f"matten_b200: `{name}` must be a CUDA tensor (there is no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"matten_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def new_flag(device) -> torch.Tensor:
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def raise_on_flag(flag: torch.Tensor):
+    """Reads the device error word (one synchronising copy per batch)."""
+    v = int(flag.item())
+    if v == 0:
+        return
+    msgs = []
+    if v & _lib.FLAG_BAD_SPECIES:
+        msgs.append("Invalid atomic numbers: a species is not in the model's allowed_species")
+    if v & _lib.FLAG_BAD_INDEX:
+        msgs.append("index out of range in edge_index / batch")
+    if v & _lib.FLAG_UNSORTED:
+        msgs.append("`batch` must be sorted (nodes of a graph contiguous)")
+    raise RuntimeError("; ".join(msgs))
+
+
+# ------------------------------------------------------------------ edges --
+def edge_vectors(pos, edge_index, edge_cell_shift=None, cell=None, batch=None, flag=None,
+                 want_vec=True, want_len=True):
+    lib = _lib.load()
+    pos = _req(pos, "pos")
+    edge_index = _req(edge_index, "edge_index", torch.int64)
+    N, E = pos.shape[0], edge_index.shape[1]
+    B = 0
+    if cell is not None:
+        cell = _req(cell, "cell", pos.dtype).view(-1, 3, 3)
+        B = cell.shape[0]
+        edge_cell_shift = _req(edge_cell_shift, "edge_cell_shift", pos.dtype)
+        if B > 1:
+            batch = _req(batch, "batch", torch.int64)
+    vec = torch.empty((E, 3), dtype=pos.dtype, device=pos.device) if want_vec else None
+    ln = torch.empty((E,), dtype=pos.dtype, device=pos.device) if want_len else None
+    check(lib.mt_edge_vectors(_dt(pos), _p(pos), _p(edge_index), _p(edge_cell_shift), _p(cell),
+                              _p(batch) if B > 1 else None, N, E, B, _p(vec), _p(ln), _p(flag), _stream(pos)))
+    _bump()
+    return vec, ln
+
+
+def edge_sh(edge_vec, lmax: int, normalize: bool = True):
+    lib = _lib.load()
+    edge_vec = _req(edge_vec, "edge_vectors")
+    E = edge_vec.shape[0]
+    out = torch.empty((E, (lmax + 1) ** 2), dtype=edge_vec.dtype, device=edge_vec.device)
+    check(lib.mt_edge_sh(_dt(edge_vec), _p(edge_vec), E, lmax, int(normalize), _p(out), _stream(edge_vec)))
+    _bump()
+    return out
+
+
+def edge_radial(edge_len, mode: int, num_basis: int, start: float, end: float, cutoff: bool = True,
+                poly_p: float = 6.0, bessel_w=None):
+    lib = _lib.load()
+    edge_len = _req(edge_len, "edge_lengths")
+    E = edge_len.shape[0]
+    if bessel_w is not None:
+        bessel_w = _req(bessel_w, "bessel_weights", edge_len.dtype)
+    out = torch.empty((E, num_basis), dtype=edge_len.dtype, device=edge_len.device)
+    check(lib.mt_edge_radial(_dt(edge_len), _p(edge_len), E, mode, num_basis, float(start), float(end),
+                             int(cutoff), float(poly_p), _p(bessel_w), _p(out), _stream(edge_len)))
+    _bump()
+    return out
+
+
+# ------------------------------------------------------------ bookkeeping --
+def csr_by_key(keys, num_keys: int, want_perm: bool = True, flag=None):
+    """Stable sort of int64 keys -> (rowptr int32 [num_keys+1], perm int32 [E] | None)."""
+    lib = _lib.load()
+    keys = _req(keys, "keys", torch.int64)
+    E = keys.shape[0]
+    rowptr = torch.empty(num_keys + 1, dtype=torch.int32, device=keys.device)
+    perm = torch.empty(E, dtype=torch.int32, device=keys.device) if want_perm else None
+    nbytes = lib.mt_csr_workspace_bytes(num_keys, E)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=keys.device)
+    check(lib.mt_csr_by_key(_p(keys), E, num_keys, _p(rowptr), _p(perm), _p(ws), nbytes, _p(flag),
+                            _stream(keys)))
+    # launches: init + per pass (hist, scan>=1, scatter) + rowptr  (approximate lower bound)
+    _bump(3 if not want_perm else 2 + 3 * max(1, ((max(num_keys, 2) - 1).bit_length() + 7) // 8))
+    return rowptr, perm
+
+
+def gather_i64_to_i32(src, perm=None):
+    lib = _lib.load()
+    src = _req(src, "src", torch.int64)
+    n = perm.shape[0] if perm is not None else src.shape[0]
+    out = torch.empty(n, dtype=torch.int32, device=src.device)
+    check(lib.mt_gather_i64_to_i32(_p(src), _p(perm), n, _p(out), _stream(src)))
+    _bump()
+    return out
+
+
+def check_sorted(keys, flag):
+    lib = _lib.load()
+    keys = _req(keys, "keys", torch.int64)
+    check(lib.mt_check_sorted(_p(keys), keys.shape[0], _p(flag), _stream(keys)))
+    _bump()
+
+
+def species_embed(atomic_numbers, species_index, lut, min_z: int, max_z: int, num_species: int,
+                  lin_w, lin_b, flag=None, want_attrs=True):
+    """Returns (species_index int64 [N], node_attrs [N,S] | None, node_feats [N,dim])."""
+    lib = _lib.load()
+    lin_w = _req(lin_w, "linear.weight")
+    lin_b = _req(lin_b, "linear.bias", lin_w.dtype)
+    dev = lin_w.device
+    z_given = atomic_numbers is not None
+    if z_given:
+        atomic_numbers = _req(atomic_numbers, "atomic_numbers", torch.int64)
+        N = atomic_numbers.shape[0]
+        lut = _req(lut, "_Z_to_index", torch.int64)
+        species_index = torch.empty(N, dtype=torch.int64, device=dev)
+    else:
+        species_index = _req(species_index, "species_index", torch.int64)
+        N = species_index.shape[0]
+    dim = lin_w.shape[0]
+    attrs = torch.empty((N, num_species), dtype=lin_w.dtype, device=dev) if want_attrs else None
+    feats = torch.empty((N, dim), dtype=lin_w.dtype, device=dev)
+    check(lib.mt_species_embed(_dt(lin_w), _p(atomic_numbers), int(z_given), _p(lut), int(min_z), int(max_z),
+                               num_species, dim, _p(lin_w), _p(lin_b), N, _p(species_index), _p(attrs),
+                               _p(feats), _p(flag), _stream(lin_w)))
+    _bump()
+    return species_index, attrs, feats
+
+
+# ------------------------------------------------------------------- conv --
+class ConvPlanHandle:
+    """Device copy of a :class:`matten_b200.plan.UVUPlan` + the POD struct of the ABI."""
+
+    def __init__(self, uvu_plan, mlp_sizes: Sequence[int], act_id: int, act_cst: float, device):
+        self.plan = uvu_plan
+        self.item_hdr = uvu_plan.item_hdr.to(device).contiguous()
+        self.slot_tab = uvu_plan.slot_tab.to(device).contiguous()
+        s = ConvPlanStruct()
+        s.x_dim, s.y_dim, s.out_dim = uvu_plan.x_dim, uvu_plan.y_dim, uvu_plan.out_dim
+        s.num_items = uvu_plan.num_items
+        s.item_hdr = self.item_hdr.data_ptr()
+        s.slot_tab = self.slot_tab.data_ptr()
+        nl = len(mlp_sizes) - 1
+        if not (1 <= nl <= _lib.MT_MAX_MLP_LAYERS):
+            raise ValueError(f"radial MLP with {nl} layers is not supported")
+        if mlp_sizes[-1] != uvu_plan.weight_numel:
+            raise ValueError("last MLP size must equal the tensor product's weight_numel")
+        s.mlp_num_layers = nl
+        for i, v in enumerate(mlp_sizes):
+            s.mlp_sizes[i] = int(v)
+        s.mlp_act = int(act_id)
+        s.mlp_act_cst = float(act_cst)
+        self.struct = s
+        self.mlp_sizes = list(mlp_sizes)
+        self.device = torch.device(device)
+
+
+def conv_fwd(handle: ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Tensor], rowptr, perm,
+             src_sorted, avg_num_neighbors: Optional[float], num_neigh=None):
+    lib = _lib.load()
+    x = _req(x, "node_features")
+    sh = _req(sh, "edge_attrs", x.dtype)
+    emb = _req(emb, "edge_embedding", x.dtype)
+    N, E = x.shape[0], sh.shape[0]
+    pl = handle.plan
+    if x.shape[1] != pl.x_dim or sh.shape[1] != pl.y_dim or emb.shape[1] != handle.mlp_sizes[0]:
+        raise ValueError(f"conv_fwd: shapes {tuple(x.shape)}, {tuple(sh.shape)}, {tuple(emb.shape)} do not match "
+                         f"the plan ({pl.x_dim}, {pl.y_dim}, {handle.mlp_sizes[0]})")
+    ws = [_req(w, f"weight_nn.layer{i}.weight", x.dtype) for i, w in enumerate(mlp_weights)]
+    for i, w in enumerate(ws):
+        if tuple(w.shape) != (handle.mlp_sizes[i], handle.mlp_sizes[i + 1]):
+            raise ValueError(f"radial MLP layer {i} has shape {tuple(w.shape)}")
+    wptrs = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+    if num_neigh is not None:
+        num_neigh = _req(num_neigh, "num_neigh", x.dtype)
+    out = torch.empty((N, pl.out_dim), dtype=x.dtype, device=x.device)
+    check(lib.mt_conv_fwd(C.byref(handle.struct), _dt(x), _p(x), _p(sh), _p(emb), wptrs, _p(rowptr), _p(perm),
+                          _p(src_sorted), float(avg_num_neighbors) if avg_num_neighbors is not None else 0.0,
+                          _p(num_neigh), _p(out), N, E, _stream(x)))
+    _bump()
+    return out
+
+
+# ----------------------------------------------------------------- linear --
+class LinPlanHandle:
+    def __init__(self, blocks, in_dim: int, out_dim: int, num_species: int, weight_numel: int):
+        self.blocks = blocks
+        arr = (LinBlockStruct * len(blocks))()
+        for i, b in enumerate(blocks):
+            arr[i].in_off, arr[i].out_off = b.in_off, b.out_off
+            arr[i].mul_in, arr[i].mul_out, arr[i].dim = b.mul_in, b.mul_out, b.dim
+            arr[i].w_off, arr[i].scale = b.w_off, b.scale
+        self.arr = arr
+        self.n = len(blocks)
+        self.in_dim, self.out_dim, self.S, self.weight_numel = in_dim, out_dim, num_species, weight_numel
+
+
+def linear_fwd(h: LinPlanHandle, x, weight, species_perm=None, species_ptr=None, out=None,
+               accumulate: bool = False):
+    lib = _lib.load()
+    x = _req(x, "x")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.shape[1] != h.in_dim:
+        raise ValueError(f"linear_fwd: input has {x2.shape[1]} features, plan expects {h.in_dim}")
+    weight = _req(weight, "weight", x.dtype)
+    if weight.numel() != h.weight_numel:
+        raise ValueError(f"linear_fwd: weight has {weight.numel()} elements, plan expects {h.weight_numel}")
+    N = x2.shape[0]
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate needs an output tensor")
+        out = torch.empty((N, h.out_dim), dtype=x.dtype, device=x.device)
+    check(lib.mt_linear_fwd(_dt(x), h.arr, h.n, h.in_dim, h.out_dim, h.S, _p(x2), _p(weight), _p(species_perm),
+                            _p(species_ptr), int(accumulate), _p(out), N, _stream(x)))
+    _bump()
+    return out.reshape(lead + (h.out_dim,))
+
+
+# ------------------------------------------------------------------- gate --
+def gate_fwd(x, in_dim: int, out_dim: int, src_idx, gate_idx, act_id, act_cst, affine_a=None, affine_b=None):
+    lib = _lib.load()
+    x = _req(x, "x")
+    if x.shape[-1] != in_dim:
+        raise ValueError(f"gate_fwd: input has {x.shape[-1]} features, expected {in_dim}")
+    lead = x.shape[:-1]
+    N = x.numel() // in_dim
+    out = torch.empty(lead + (out_dim,), dtype=x.dtype, device=x.device)
+    check(lib.mt_gate_fwd(_dt(x), _p(x), in_dim, out_dim, _p(src_idx), _p(gate_idx), _p(act_id), _p(act_cst),
+                          _p(affine_a), _p(affine_b), _p(out), N, _stream(x)))
+    _bump()
+    return out
+
+
+# ------------------------------------------------------------------- pool --
+_MODES = {"sum": 0, "add": 0, "mean": 1, "min": 2, "max": 3}
+
+
+def segment_reduce(x, ptr, reduce: str = "sum"):
+    lib = _lib.load()
+    x = _req(x, "x")
+    B = ptr.shape[0] - 1
+    dim = x.shape[1]
+    out = torch.empty((B, dim), dtype=x.dtype, device=x.device)
+    check(lib.mt_segment_reduce(_dt(x), _p(x), _p(ptr), dim, B, _MODES[reduce], _p(out), _stream(x)))
+    _bump()
+    return out

@@ -1,0 +1,128 @@
+"""Host-side planning of the product (matten_b200/o3.py, plan.py) against the independent oracle
+restatement, and the bookkeeping numbers of SURVEY.md Appendix A."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from matten_b200 import o3
+from matten_b200.codegen.gen_tables import cg_nnz, cg_types
+from matten_b200.plan import GatePlan, UVUPlan, linear_blocks
+from oracle import e3nn_restated as E
+from oracle import matten_restated as M
+from tests.helpers import HP_LMAX2, HP_LMAX4, HP_REFTEST, SPECIES8
+
+
+def test_irreps_algebra():
+    ir = o3.Irreps("32x0o+32x0e + 16x1o+16x1e + 4x2o+4x2e")
+    assert ir.dim == 200 and ir.num_irreps == 104 and ir.lmax == 2
+    assert str(o3.Irreps("1e + 0e + 1e").sort().irreps) == "1x0e+1x1e+1x1e"
+    assert o3.Irreps("2o + 1e + 0e + 1e").sort().p == (3, 1, 0, 2)
+    assert str(o3.Irreps("0e+0o").sort().irreps) == "1x0o+1x0e"
+    assert str((o3.Irreps("3x0e") + o3.Irreps("2x0e+1o")).simplify()) == "5x0e+1x1o"
+    assert [str(i) for i in o3.Irrep("1o") * o3.Irrep("2e")] == ["1o", "2o", "3o"]
+    assert o3.Irrep("2e") in o3.Irreps("4x2e") and o3.Irrep("2o") not in o3.Irreps("4x2e")
+    assert str(o3.Irreps.spherical_harmonics(2)) == "1x0e+1x1o+1x2e"
+    assert (o3.Irrep(0, 1) == o3.Irreps("0e")) is False  # the always-False clause of utils.py:210
+
+
+def test_wigner_matches_oracle():
+    for l1, l2, l3 in cg_types():
+        assert (o3.wigner_3j(l1, l2, l3) - E.wigner_3j(l1, l2, l3)).abs().max() < 1e-14
+
+
+def test_cg_nnz_table():
+    # SURVEY.md App. A
+    expect = {(0, 0, 0): 1, (0, 1, 1): 3, (1, 1, 1): 6, (1, 1, 2): 11, (1, 2, 2): 16, (1, 2, 3): 21, (2, 2, 2): 25,
+              (2, 2, 4): 37, (3, 3, 3): 42, (3, 3, 4): 67, (4, 4, 4): 97, (2, 3, 4): 50, (4, 4, 2): 61}
+    for k, v in expect.items():
+        assert cg_nnz(*k) == v, k
+    assert len(cg_types()) == 65
+
+
+@pytest.mark.parametrize("formula", ["ijkl=jikl=klij", "ij=ji", "ij", "ij=-ji", "ijk=jik"])
+def test_cartesian_tensor_matches_oracle(formula):
+    ct = o3.CartesianTensor(formula)
+    ir, Q = E.reduced_tensor_products(formula)
+    assert o3.parse_irreps_list(ct) == ir
+    assert np.abs(ct.change_of_basis(torch.float64).numpy() - Q.reshape(Q.shape[0], -1)).max() < 1e-12
+
+
+def test_normalize2mom_matches_oracle():
+    import torch.nn.functional as F
+
+    assert o3.normalize2mom_const(F.silu) == E.normalize2mom(F.silu).cst
+    assert o3.normalize2mom_const(torch.tanh) == E.normalize2mom(torch.tanh).cst
+    assert o3.normalize2mom_const(torch.sigmoid) == E.normalize2mom(torch.sigmoid).cst
+
+
+@pytest.mark.parametrize("hp,expect", [
+    (HP_LMAX2, [(3, 48, 144, 288), (15, 216, 696, 2096), (27, 336, 1104, 3616), (30, 432, 1392, 4192)]),
+    (HP_LMAX4, [(5, 80, 400, 800), (59, 452, 2324, 9854), (99, 714, 3658, 16632), (103, 842, 4170, 17656)]),
+    (HP_REFTEST, [(5, 160, 800, None), (65, 608, 3328, None), (125, 1056, 5856, None), (130, 1216, 6656, None)]),
+])
+def test_uvu_plan_matches_appendix_a_and_oracle(hp, expect):
+    from matten_b200.model_factory import ScalarTensorModel
+
+    species = SPECIES8 if hp is not HP_REFTEST else [8, 52]
+    prod = ScalarTensorModel(hp, {"allowed_species": species})
+    orac = M.ScalarTensorModel(hp, {"allowed_species": species})
+    got = []
+    for (n1, m1), (n2, m2) in zip(prod.backbone.named_children(), orac.backbone.named_children()):
+        assert n1 == n2
+        p1, p2 = getattr(m1, "conv", m1), getattr(m2, "conv", m2)
+        if not hasattr(p1, "tp"):
+            continue
+        plan = p1.tp.plan
+        got.append((len(plan.paths), plan.weight_numel, plan.out_dim, plan.cg_macs_per_edge()))
+        # same instructions, same sorted mid irreps, same offsets as the oracle's e3nn-style TP
+        tp = p2.tp.tp
+        assert o3.parse_irreps_list(plan.irreps_mid) == tp.irreps_out
+        assert [(p.i_in1, p.i_in2, p.i_out) for p in plan.paths] == [(i.i_in1, i.i_in2, i.i_out)
+                                                                      for i in tp.instructions]
+        assert all(abs(i.path_weight - math.sqrt(2 * tp.irreps_out[i.i_out][1] + 1)) < 1e-12
+                   for i in tp.instructions)
+        assert o3.parse_irreps_list(m1.irreps_out["node_features"]) == \
+            [tuple(t) for t in m2.irreps_out["node_features"]]
+        # every weight column appears exactly once in the slot table
+        cols = plan.slot_tab[:, :, 0].reshape(-1)
+        cols = cols[cols >= 0]
+        per_item_cols = [set(plan.slot_tab[i, :, 0][plan.slot_tab[i, :, 0] >= 0].tolist())
+                         for i in range(plan.num_items)]
+        assert sorted(set().union(*per_item_cols)) == list(range(plan.weight_numel))
+        assert sum(len(s) for s in per_item_cols) == plan.weight_numel
+    for g, e in zip(got, expect):
+        assert g[:3] == e[:3]
+        if e[3] is not None:
+            assert g[3] == e[3]
+    # state_dict keys/shapes are interchangeable
+    sd_p, sd_o = prod.state_dict(), orac.state_dict()
+    for k, v in sd_p.items():
+        assert k in sd_o and tuple(sd_o[k].shape) == tuple(v.shape), k
+
+
+def test_linear_blocks_scales():
+    blocks, numel = linear_blocks("54x0o+56x0e+100x1o", "32x0o+32x0e+16x1o+4x2e", 8)
+    assert numel == (54 * 32 + 56 * 32 + 100 * 16) * 8
+    real = [b for b in blocks if b.mul_in > 0]
+    assert [round(b.scale, 12) for b in real] == [round(1 / math.sqrt(8 * m), 12) for m in (54, 56, 100)]
+    zero = [b for b in blocks if b.mul_in == 0]
+    assert len(zero) == 1 and zero[0].mul_out == 4 and zero[0].dim == 5
+    # o3.Linear with two inputs feeding one output: fan-in is summed
+    blocks, numel = linear_blocks("4x0e+6x0e", "3x0e", 1)
+    assert numel == 30 and all(abs(b.scale - 1 / math.sqrt(10)) < 1e-12 for b in blocks)
+
+
+def test_gate_plan_irreps():
+    sh = "0e+1o+2e+3o+4e"
+    g = GatePlan("16x0e", sh, HP_LMAX4["conv_layer_irreps"], {1: "silu", -1: "tanh"}, {1: "sigmoid", -1: "tanh"})
+    assert str(g.irreps_in) == "56x0e+16x1o+4x2e+2x3o+2x4e"
+    assert g.irreps_in.dim == 156 and g.irreps_out.dim == 132
+    g = GatePlan("32x0e+16x1o+4x2e+2x3o+2x4e", sh, HP_LMAX4["conv_layer_irreps"], {1: "silu", -1: "tanh"},
+                 {1: "sigmoid", -1: "tanh"})
+    assert g.irreps_in.dim == 260 and g.irreps_out.dim == 214
+    g = GatePlan(g.irreps_out, sh, HP_LMAX4["conv_layer_irreps"], {1: "silu", -1: "tanh"},
+                 {1: "sigmoid", -1: "tanh"})
+    assert str(g.irreps_in) == "32x0o+78x0e+16x1o+16x1e+4x2o+4x2e+2x3o+2x3e+2x4e"
+    assert g.irreps_in.dim == 292 and g.irreps_out.dim == 246
