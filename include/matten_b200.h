@@ -71,6 +71,8 @@ typedef void* mt_stream; /* cudaStream_t */
 
 int mt_abi_version(void);
 const char* mt_last_error(void);
+/* Number of kernels this library has launched in this process (all threads). */
+uint64_t mt_launch_count(void);
 /* MT_OK if `device` is compute capability 10.x, else MT_EARCH. */
 int mt_device_supported(int device);
 

@@ -46,6 +46,7 @@ _V, _I, _L, _D, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t
 SIGNATURES = {
     "mt_abi_version": (_I, []),
     "mt_last_error": (C.c_char_p, []),
+    "mt_launch_count": (C.c_uint64, []),
     "mt_device_supported": (_I, [_I]),
     "mt_edge_vectors": (_I, [_I, _V, _V, _V, _V, _V, _L, _L, _L, _V, _V, _V, _V]),
     "mt_edge_sh": (_I, [_I, _V, _L, _I, _I, _V, _V]),

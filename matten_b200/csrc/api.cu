@@ -1,9 +1,13 @@
 // Error handling, version and device gate of the C ABI (include/matten_b200.h).
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace mt {
+
+uint64_t launch_count();
 
 char* last_error_buf() {
   static thread_local char buf[512] = {0};
@@ -17,6 +21,10 @@ int set_error(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int check_device() {
   int dev = 0;
@@ -46,6 +54,8 @@ extern "C" {
 int mt_abi_version(void) { return MT_ABI_VERSION; }
 
 const char* mt_last_error(void) { return mt::last_error_buf(); }
+
+uint64_t mt_launch_count(void) { return mt::launch_count(); }
 
 int mt_device_supported(int device) {
   int major = 0;

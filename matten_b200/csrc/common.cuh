@@ -11,6 +11,7 @@ namespace mt {
 
 // ----------------------------------------------------------------- errors --
 char* last_error_buf();  // thread-local, defined in api.cu
+void count_launch();     // bumps the process-wide kernel-launch counter (mt_launch_count)
 int set_error(int code, const char* fmt, ...);
 int check_device();  // MT_OK iff current device is cc 10.x
 
@@ -28,6 +29,7 @@ int check_device();  // MT_OK iff current device is cc 10.x
     if (_e != cudaSuccess)                                                            \
       return ::mt::set_error(MT_ECUDA, "kernel launch failed: %s (%s:%d)",            \
                              cudaGetErrorString(_e), __FILE__, __LINE__);             \
+    ::mt::count_launch();                                                             \
   } while (0)
 
 #define MT_REQUIRE(cond, ...)                                                         \

@@ -215,27 +215,16 @@ using namespace mt;
 
 extern "C" {
 
-int mt_linear_fwd(int dtype, const mt_lin_block* blocks, int num_blocks, int in_dim, int out_dim,
-                  int num_species, const void* x, const void* weight, const int32_t* species_perm,
-                  const int32_t* species_ptr, int accumulate, void* out, int64_t N, mt_stream stream) {
-  MT_ENTRY_GUARD();
-  MT_REQUIRE(blocks && num_blocks > 0 && num_blocks <= kLinMaxBlocks, "num_blocks %d not in 1..%d", num_blocks,
-             kLinMaxBlocks);
-  MT_REQUIRE(in_dim > 0 && out_dim > 0 && num_species >= 1, "bad dims");
-  MT_REQUIRE((species_perm == nullptr) == (species_ptr == nullptr), "species_perm/ptr must be given together");
-  MT_REQUIRE(num_species == 1 || species_ptr != nullptr, "species grouping required when num_species > 1");
-  if (N == 0) return MT_OK;
-  MT_REQUIRE(x && out, "null pointer");
+static int linear_fwd_round(int dtype, const mt_lin_block* const* blocks, int num_blocks, int in_dim,
+                            int out_dim, int num_species, const void* x, const void* weight,
+                            const int32_t* species_perm, const int32_t* species_ptr, int accumulate, void* out,
+                            int64_t N, cudaStream_t st) {
   LinParams p;
   memset(&p, 0, sizeof(p));
   p.num_blocks = num_blocks;
   int64_t total = 0;
   for (int b = 0; b < num_blocks; ++b) {
-    const mt_lin_block& k = blocks[b];
-    MT_REQUIRE(k.dim >= 1 && k.dim <= kLinRows && k.mul_out > 0 && k.mul_in >= 0, "bad linear block %d", b);
-    MT_REQUIRE(k.out_off >= 0 && k.out_off + k.mul_out * k.dim <= out_dim, "block %d exceeds out_dim", b);
-    MT_REQUIRE(k.mul_in == 0 || (k.in_off >= 0 && k.in_off + k.mul_in * k.dim <= in_dim), "block %d exceeds in_dim", b);
-    MT_REQUIRE(k.mul_in == 0 || weight != nullptr, "null weight");
+    const mt_lin_block& k = *blocks[b];
     p.in_off[b] = k.in_off; p.out_off[b] = k.out_off; p.mul_in[b] = k.mul_in; p.mul_out[b] = k.mul_out;
     p.dim[b] = k.dim; p.w_off[b] = k.w_off; p.scale[b] = k.scale;
     int tn = kLinRows / k.dim;
@@ -252,9 +241,54 @@ int mt_linear_fwd(int dtype, const mt_lin_block* blocks, int num_blocks, int in_
   p.x = x; p.weight = weight; p.sperm = species_perm; p.sptr = species_ptr;
   p.accumulate = accumulate; p.out = out; p.N = N;
   MT_DISPATCH_DTYPE(dtype, {
-    linear_fwd_kernel<T><<<(unsigned)total, 256, 0, as_stream(stream)>>>(p);
+    linear_fwd_kernel<T><<<(unsigned)total, 256, 0, st>>>(p);
   });
   MT_LAUNCH_OK();
+  return MT_OK;
+}
+
+int mt_linear_fwd(int dtype, const mt_lin_block* blocks, int num_blocks, int in_dim, int out_dim,
+                  int num_species, const void* x, const void* weight, const int32_t* species_perm,
+                  const int32_t* species_ptr, int accumulate, void* out, int64_t N, mt_stream stream) {
+  MT_ENTRY_GUARD();
+  MT_REQUIRE(blocks && num_blocks > 0 && num_blocks <= 4 * kLinMaxBlocks, "num_blocks %d not in 1..%d",
+             num_blocks, 4 * kLinMaxBlocks);
+  MT_REQUIRE(in_dim > 0 && out_dim > 0 && num_species >= 1, "bad dims");
+  MT_REQUIRE((species_perm == nullptr) == (species_ptr == nullptr), "species_perm/ptr must be given together");
+  MT_REQUIRE(num_species == 1 || species_ptr != nullptr, "species grouping required when num_species > 1");
+  if (N == 0) return MT_OK;
+  MT_REQUIRE(x && out, "null pointer");
+  for (int b = 0; b < num_blocks; ++b) {
+    const mt_lin_block& k = blocks[b];
+    MT_REQUIRE(k.dim >= 1 && k.dim <= kLinRows && k.mul_out > 0 && k.mul_in >= 0, "bad linear block %d", b);
+    MT_REQUIRE(k.out_off >= 0 && k.out_off + k.mul_out * k.dim <= out_dim, "block %d exceeds out_dim", b);
+    MT_REQUIRE(k.mul_in == 0 || (k.in_off >= 0 && k.in_off + k.mul_in * k.dim <= in_dim), "block %d exceeds in_dim", b);
+    MT_REQUIRE(k.mul_in == 0 || weight != nullptr, "null weight");
+  }
+  // Blocks that write the same output range (several input irreps of one type feeding one output,
+  // e3nn sums them) must not race: round r holds the r-th block of every distinct output range;
+  // rounds after the first accumulate.  Simplified irreps (every matten model) need one round.
+  int round_of[4 * kLinMaxBlocks];
+  int max_round = 0;
+  for (int b = 0; b < num_blocks; ++b) {
+    int r = 0;
+    for (int c = 0; c < b; ++c)
+      if (blocks[c].out_off == blocks[b].out_off) ++r;
+    round_of[b] = r;
+    if (r > max_round) max_round = r;
+  }
+  for (int r = 0; r <= max_round; ++r) {
+    const mt_lin_block* sel[kLinMaxBlocks];
+    int n = 0;
+    for (int b = 0; b < num_blocks; ++b) {
+      if (round_of[b] != r) continue;
+      MT_REQUIRE(n < kLinMaxBlocks, "more than %d linear blocks in one round", kLinMaxBlocks);
+      sel[n++] = &blocks[b];
+    }
+    int rc = linear_fwd_round(dtype, sel, n, in_dim, out_dim, num_species, x, weight, species_perm, species_ptr,
+                              (accumulate || r > 0) ? 1 : 0, out, N, as_stream(stream));
+    if (rc != MT_OK) return rc;
+  }
   return MT_OK;
 }
 

@@ -16,13 +16,17 @@ import torch
 from . import _lib
 from ._lib import ConvPlanStruct, LinBlockStruct, MT_F32, MT_F64, check
 
-#: number of kernel launches issued through this module (bench.py reports it)
-LAUNCHES = 0
+def launch_count() -> int:
+    """Kernels launched by libmatten_b200.so in this process (exact, counted in the library)."""
+    return int(_lib.load().mt_launch_count())
+
+
+#: optional profiling hook: when set to a list, conv_fwd appends (tag, start_event, end_event)
+CONV_EVENTS = None
 
 
 def _bump(n: int = 1):
-    global LAUNCHES
-    LAUNCHES += n
+    pass
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -221,10 +225,16 @@ def conv_fwd(handle: ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Ten
     if num_neigh is not None:
         num_neigh = _req(num_neigh, "num_neigh", x.dtype)
     out = torch.empty((N, pl.out_dim), dtype=x.dtype, device=x.device)
+    if CONV_EVENTS is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib.mt_conv_fwd(C.byref(handle.struct), _dt(x), _p(x), _p(sh), _p(emb), wptrs, _p(rowptr), _p(perm),
                           _p(src_sorted), float(avg_num_neighbors) if avg_num_neighbors is not None else 0.0,
                           _p(num_neigh), _p(out), N, E, _stream(x)))
-    _bump()
+    if CONV_EVENTS is not None:
+        ev1.record()
+        CONV_EVENTS.append(((pl.x_dim, pl.y_dim, pl.out_dim, pl.weight_numel, N, E), ev0, ev1))
     return out
 
 
