@@ -169,6 +169,22 @@ typedef struct {
   int32_t mlp_sizes[MT_MAX_MLP_LAYERS + 1];
   int32_t mlp_act;      /* mt_act of the hidden layers              */
   double mlp_act_cst;   /* normalize2mom constant of that activation */
+  /* Optional tables of the tcgen05 path (fp32, last hidden size <= 32, <= 512 TMEM rows); tc_num_tiles
+   * == 0 disables it.  The weight columns are laid out as rows of the MMA A operand in groups of 32
+   * TMEM lanes ("quarters" of a 128-row tile), one (l1,l2,l3) type per group or several small types
+   * packed into one group as lane-phased sub-items:
+   *   tc_row_wcol [tc_num_tiles*128]   : weight column of every A row (-1 = zero row)
+   *   tc_sub_hdr  [tc_num_sub,8]       : {cg_type_id, cols_per_warp, first TMEM lane in the quarter,
+   *                                       tile, quarter, 0, 0, 0}
+   *   tc_sub_slot [tc_num_sub,32,4]    : per lane {x offset, sh offset, out offset, valid}
+   *   tc_q_list   [4,64], tc_q_count[4]: sub-items of every quarter, heaviest first            */
+  int32_t tc_num_tiles;
+  int32_t tc_num_sub;
+  const int32_t* tc_row_wcol; /* device */
+  const int32_t* tc_sub_hdr;  /* device */
+  const int32_t* tc_sub_slot; /* device */
+  const int32_t* tc_q_list;   /* device */
+  int32_t tc_q_count[4];
 } mt_conv_plan;
 
 /* x [N,x_dim]; sh [E,y_dim], emb [E,mlp_sizes[0]] in ORIGINAL edge order;

@@ -29,6 +29,9 @@ class ConvPlanStruct(C.Structure):
         ("item_hdr", C.c_void_p), ("slot_tab", C.c_void_p),
         ("mlp_num_layers", C.c_int32), ("mlp_sizes", C.c_int32 * (MT_MAX_MLP_LAYERS + 1)),
         ("mlp_act", C.c_int32), ("mlp_act_cst", C.c_double),
+        ("tc_num_tiles", C.c_int32), ("tc_num_sub", C.c_int32),
+        ("tc_row_wcol", C.c_void_p), ("tc_sub_hdr", C.c_void_p), ("tc_sub_slot", C.c_void_p),
+        ("tc_q_list", C.c_void_p), ("tc_q_count", C.c_int32 * 4),
     ]
 
 

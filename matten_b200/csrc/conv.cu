@@ -14,6 +14,11 @@ MT_DECL(float, 8) MT_DECL(float, 16) MT_DECL(float, 32) MT_DECL(float, 64)
 MT_DECL(double, 8) MT_DECL(double, 16) MT_DECL(double, 32) MT_DECL(double, 64)
 #undef MT_DECL
 
+int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, const void* emb,
+                    const void* const* mlp_weights, const int32_t* rowptr, const int32_t* perm,
+                    const int32_t* src_sorted, double avg, const void* num_neigh, void* out, int64_t N, int64_t E,
+                    cudaStream_t st, int* used);
+
 static int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;
@@ -75,7 +80,7 @@ static int conv_fwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
 
   // chunk size from the shared-memory budget
   const size_t per_edge = (size_t)(2 * hp_max + p.xs_stride + p.y_dim) * sizeof(T);
-  size_t budget = (size_t)env_int("MT_CONV_SMEM_KB", sizeof(T) == 4 ? 72 : 100) * 1024;
+  size_t budget = (size_t)env_int("MT_CONV_SMEM_KB", sizeof(T) == 4 ? 64 : 96) * 1024;
   int EC = (int)(budget / per_edge);
   EC = EC / 8 * 8;
   if (EC > 256) EC = 256;
@@ -87,14 +92,18 @@ static int conv_fwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
   if (TN < 1) TN = 1;
   if (TN > 32) TN = 32;
   p.tile_nodes = env_int("MT_CONV_TN", TN);
-  const size_t smem = (size_t)EC * per_edge;
+  size_t hidden_w = 0;
+  for (int i = 0; i + 1 < p.nl; ++i) hidden_w += (size_t)p.sizes[i] * p.sizes[i + 1];
+  const size_t smem = (size_t)EC * per_edge + hidden_w * sizeof(T);
   MT_REQUIRE(smem <= 227 * 1024, "conv tile needs %zu bytes of shared memory", smem);
   const int threads = env_int("MT_CONV_THREADS", 256);
   MT_REQUIRE(threads >= 32 && threads <= 256 && threads % 32 == 0, "MT_CONV_THREADS must be 32..256");
   int64_t tiles = ceil_div<int64_t>(N, p.tile_nodes);
   int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
-  if (ctas_per_sm > 8) ctas_per_sm = 8;
+  const int reg_limit = sizeof(T) == 4 ? (HP <= 32 ? 3 : 2) : 1;  // conv_fwd_min_blocks<T, HP>()
+  if (ctas_per_sm > reg_limit) ctas_per_sm = reg_limit;
+  ctas_per_sm = env_int("MT_CONV_CTAS_PER_SM", ctas_per_sm);
   int64_t grid = (int64_t)kNumSMs * ctas_per_sm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
@@ -126,6 +135,20 @@ int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* 
   MT_REQUIRE(E == 0 || (sh && emb && perm && src_sorted), "null edge pointer");
   MT_REQUIRE(num_neigh != nullptr || avg_num_neighbors > 0.0, "avg_num_neighbors must be > 0");
   for (int i = 0; i < plan->mlp_num_layers; ++i) MT_REQUIRE(mlp_weights[i] != nullptr, "null MLP weight %d", i);
+  // fp32: Blackwell tensor-core path (radial MLP on tcgen05, weights in TMEM) when the plan qualifies;
+  // MT_CONV_IMPL=fma forces the FMA-pipe kernel (used by the tests to cross-check the two)
+  if (dtype == MT_F32) {
+    const char* impl = getenv("MT_CONV_IMPL");
+    if (!(impl && strcmp(impl, "fma") == 0)) {
+      int used = 0;
+      rc = conv_fwd_tc_try(plan, x, sh, emb, mlp_weights, rowptr, perm, src_sorted, avg_num_neighbors, num_neigh,
+                           out, N, E, as_stream(stream), &used);
+      if (rc != MT_OK) return rc;
+      if (used) return MT_OK;
+      if (impl && strcmp(impl, "tc") == 0)
+        return set_error(MT_EINVAL, "MT_CONV_IMPL=tc but this plan/shape does not qualify for the tcgen05 path");
+    }
+  }
   MT_DISPATCH_DTYPE(dtype, {
     return conv_fwd_impl<T>(plan, x, sh, emb, mlp_weights, rowptr, perm, src_sorted, avg_num_neighbors,
                             num_neigh, out, N, E, as_stream(stream));

@@ -117,14 +117,21 @@ __device__ __forceinline__ void conv_unit(const T (&wreg)[HP], const T* __restri
   }
 }
 
+// resident CTAs per SM the register budget is compiled for
 template <typename T, int HP>
-__global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvFwdParams p) {
+__host__ __device__ constexpr int conv_fwd_min_blocks() {
+  return sizeof(T) == 4 ? (HP <= 32 ? 3 : 2) : 1;
+}
+
+template <typename T, int HP>
+__global__ void __launch_bounds__(256, (conv_fwd_min_blocks<T, HP>())) conv_fwd_kernel(const ConvFwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int EC = p.chunk_edges;
   T* ha = reinterpret_cast<T*>(smem_raw);
   T* hb = ha + (size_t)EC * p.hp_max;
   T* xs = hb + (size_t)EC * p.hp_max;
   T* ys = xs + (size_t)EC * p.xs_stride;
+  T* wh = ys + (size_t)EC * p.y_dim;  // hidden-layer weights, pre-scaled by 1/sqrt(fan_in)
   __shared__ int s_counter;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -136,6 +143,18 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvFwdParams p) {
   const T* __restrict__ Wlast = static_cast<const T*>(p.w[p.nl - 1]);
   const int Wn = p.sizes[p.nl];
   const T inv_sqrt_h = T(1) / sqrt(T(H_last));
+
+  {
+    int off = 0;
+    for (int li = 0; li + 1 < p.nl; ++li) {
+      const int fi = p.sizes[li], fo = p.sizes[li + 1];
+      const T* __restrict__ Wl = static_cast<const T*>(p.w[li]);
+      const T s = T(1) / sqrt(T(fi));
+      for (int t = threadIdx.x; t < fi * fo; t += blockDim.x) wh[off + t] = Wl[t] * s;
+      off += fi * fo;
+    }
+  }
+  __syncthreads();
 
   const int64_t num_tiles = ceil_div<int64_t>(p.N, p.tile_nodes);
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -169,10 +188,11 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvFwdParams p) {
       // hidden layers of the radial MLP: act(h @ W / sqrt(fan_in)) * cst
       T* hin = ha;
       T* hout = hb;
+      int woff = 0;
       for (int li = 0; li + 1 < p.nl; ++li) {
         const int fi = p.sizes[li], fo = p.sizes[li + 1];
-        const T* __restrict__ Wl = static_cast<const T*>(p.w[li]);
-        const T s = T(1) / sqrt(T(fi));
+        const T* Wl = wh + woff;
+        woff += fi * fo;
         const T cst = T(p.act_cst);
         for (int t = tid; t < ne * p.hp_max; t += blockDim.x) {
           int el = t / p.hp_max, j = t - el * p.hp_max;
@@ -180,7 +200,7 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvFwdParams p) {
           if (j < fo) {
             const T* hr = hin + (size_t)el * p.hp_max;
             T a = T(0);
-            for (int k = 0; k < fi; ++k) a = fma(hr[k], Wl[(size_t)k * fo + j] * s, a);
+            for (int k = 0; k < fi; ++k) a = fma(hr[k], Wl[k * fo + j], a);
             v = apply_act<T>(p.act, a) * cst;
           }
           hout[t] = v;

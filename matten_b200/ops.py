@@ -201,6 +201,15 @@ class ConvPlanHandle:
             s.mlp_sizes[i] = int(v)
         s.mlp_act = int(act_id)
         s.mlp_act_cst = float(act_cst)
+        s.tc_num_tiles = 0
+        if getattr(uvu_plan, "tc_num_tiles", 0) > 0:
+            self.tc_tables = [t.to(device).contiguous() for t in (uvu_plan.tc_row_wcol, uvu_plan.tc_sub_hdr,
+                                                                   uvu_plan.tc_sub_slot, uvu_plan.tc_q_list)]
+            s.tc_num_tiles = uvu_plan.tc_num_tiles
+            s.tc_num_sub = uvu_plan.tc_num_sub
+            s.tc_row_wcol, s.tc_sub_hdr, s.tc_sub_slot, s.tc_q_list = [t.data_ptr() for t in self.tc_tables]
+            for q in range(4):
+                s.tc_q_count[q] = uvu_plan.tc_q_count[q]
         self.struct = s
         self.mlp_sizes = list(mlp_sizes)
         self.device = torch.device(device)

@@ -74,6 +74,7 @@ class UVUPlan:
         self.weight_numel = w_off
         self.x_dim, self.y_dim, self.out_dim = in1.dim, in2.dim, self.irreps_mid.dim
         self._build_items()
+        self._build_tc()
 
     @property
     def irreps_out(self) -> Irreps:
@@ -103,6 +104,82 @@ class UVUPlan:
         self.num_items = len(items)
         self.item_hdr = torch.tensor([[t[1], t[2]] for t in items], dtype=torch.int32)
         self.slot_tab = torch.tensor([t[3] for t in items], dtype=torch.int32).reshape(self.num_items, 32, 4)
+
+    def _build_tc(self):
+        """Tables of the tcgen05 path (csrc/conv_fwd_tc.cuh).  Weight columns become rows of the MMA A
+        operand in groups of 32 TMEM lanes (one warp "quarter" of a 128-row tile).  A type's columns are cut
+        into full groups of 32 (one sub-item, lane == row) plus a remainder that is padded to cpw = 8 or 16
+        lanes and packed with other small remainders into shared groups; a packed sub-item runs on all 32
+        lanes as (column, edge-phase) pairs.  Groups are spread over the 4 quarters to balance their cost."""
+        by_type = {}
+        for p in self.paths:
+            cols = by_type.setdefault((p.l1, p.l2, p.l3), [])
+            for u in range(p.mul):
+                cols.append((p.w_off + u, p.x_off + u * (2 * p.l1 + 1), p.y_off, p.out_off + u * (2 * p.l3 + 1)))
+        subs = []  # dict(type, cpw, cols, cost)
+        for (l1, l2, l3), cols in by_type.items():
+            base = cg_nnz(l1, l2, l3) * 1.5 + 2 * l1 + 2 * l2 + 2 * l3 + 9
+            for c0 in range(0, len(cols), 32):
+                chunk = cols[c0:c0 + 32]
+                cpw = 32 if len(chunk) > 16 else (16 if len(chunk) > 8 else 8)
+                subs.append({"type": cg_type_id(l1, l2, l3), "cpw": cpw, "cols": chunk, "cost": base * cpw / 32.0})
+        # pack: cpw == 32 sub-items own a group; smaller ones share groups (first fit, large first)
+        groups = []  # list of list of (sub index, lane0)
+        for i, sb in enumerate(subs):
+            if sb["cpw"] == 32:
+                groups.append({"subs": [(i, 0)], "used": 32})
+        small = sorted([i for i, sb in enumerate(subs) if sb["cpw"] < 32], key=lambda i: -subs[i]["cpw"])
+        packed = []
+        for i in small:
+            for g in packed:
+                if g["used"] + subs[i]["cpw"] <= 32:
+                    g["subs"].append((i, g["used"]))
+                    g["used"] += subs[i]["cpw"]
+                    break
+            else:
+                packed.append({"subs": [(i, 0)], "used": subs[i]["cpw"]})
+        groups += packed
+        MT = (len(groups) + 3) // 4
+        self.tc_num_tiles = 0
+        if MT > 4 or len(subs) > 64:
+            return  # does not fit 512 TMEM rows: the FMA-pipe kernel handles this plan
+        for g in groups:
+            g["cost"] = sum(subs[i]["cost"] for i, _ in g["subs"])
+        groups.sort(key=lambda g: -g["cost"])
+        qcost, qn = [0.0] * 4, [0] * 4
+        row_wcol = [-1] * (MT * 128)
+        hdr = [[0] * 8 for _ in subs]
+        slot = [[[0, 0, 0, 0] for _ in range(32)] for _ in subs]
+        qlist = [[] for _ in range(4)]
+        for g in groups:
+            q = min((q for q in range(4) if qn[q] < MT), key=lambda q: qcost[q])
+            t = qn[q]
+            qn[q] += 1
+            qcost[q] += g["cost"]
+            for i, lane0 in g["subs"]:
+                sb = subs[i]
+                hdr[i] = [sb["type"], sb["cpw"], lane0, t, q, 0, 0, 0]
+                for j, (wc, xo, yo, oo) in enumerate(sb["cols"]):
+                    row_wcol[t * 128 + q * 32 + lane0 + j] = wc
+                for lane in range(32):
+                    j = lane % sb["cpw"]
+                    if j < len(sb["cols"]):
+                        _, xo, yo, oo = sb["cols"][j]
+                        slot[i][lane] = [xo, yo, oo, 1]
+                qlist[q].append(i)
+        for q in range(4):
+            qlist[q].sort(key=lambda i: -subs[i]["cost"])
+        self.tc_num_tiles = MT
+        self.tc_num_sub = len(subs)
+        self.tc_row_wcol = torch.tensor(row_wcol, dtype=torch.int32)
+        self.tc_sub_hdr = torch.tensor(hdr, dtype=torch.int32)
+        self.tc_sub_slot = torch.tensor(slot, dtype=torch.int32)
+        ql = torch.zeros((4, 64), dtype=torch.int32)
+        for q in range(4):
+            ql[q, :len(qlist[q])] = torch.tensor(qlist[q], dtype=torch.int32)
+        self.tc_q_list = ql
+        self.tc_q_count = [len(qlist[q]) for q in range(4)]
+        self.tc_q_cost = qcost
 
     # per-edge algorithmic cost, for roofline reporting (SURVEY.md section 8d)
     def cg_macs_per_edge(self) -> int:

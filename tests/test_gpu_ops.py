@@ -337,3 +337,49 @@ def test_conv_mlp_variants(dev, dtype):
     _conv_case(dev, dtype, ir, 2, ir, 3, 8, 64, 2, 10.0, 64, lambda n: 12, 6)
     _conv_case(dev, dtype, ir, 2, ir, 1, 10, 8, 0, 10.0, 64, lambda n: 12, 7)
     _conv_case(dev, dtype, ir, 1, ir, 3, 8, 16, 3, 10.0, 64, lambda n: 12, 8)
+
+
+# ------------------------------------------------------------------ tcgen05 path of the convolution
+def _with_impl(impl, fn):
+    import os
+
+    old = os.environ.get("MT_CONV_IMPL")
+    os.environ["MT_CONV_IMPL"] = impl
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ["MT_CONV_IMPL"]
+        else:
+            os.environ["MT_CONV_IMPL"] = old
+
+
+@pytest.mark.parametrize("impl", ["tc", "fma"])
+def test_conv_tensor_core_and_fma_paths(dev, impl):
+    """Both fp32 implementations of mt_conv_fwd (tcgen05 radial MLP + TMEM weights, and the FMA-pipe
+    kernel) against the oracle: the bench layers, packed small types, ragged degrees (empty nodes,
+    exactly 64 / 65 / 500 edges: chunk boundaries and split nodes), per-node normalisation."""
+    ir = "32x0o+32x0e+16x1o+16x1e+4x2o+4x2e"
+    f32 = torch.float32
+    deg = lambda n: [0, 1, 3, 500, 28, 0, 64, 65, 63, 2, 130, 0][n % 12]  # noqa: E731
+
+    def run():
+        _conv_case(dev, f32, "16x0e", 2, "52x0e+16x1o+4x2e", 8, 8, 32, 2, 28.0, 300, lambda n: 28, 10)
+        _conv_case(dev, f32, "32x0e+16x1o+4x2e", 2, "72x0e+16x1o+16x1e+4x2o+4x2e", 8, 8, 32, 2, 28.0, 300,
+                   lambda n: 27 + (n % 3), 11)
+        _conv_case(dev, f32, ir, 2, ir, 8, 8, 32, 2, 28.0, 333, lambda n: 28, 12)
+        _conv_case(dev, f32, ir, 2, ir, 4, 8, 32, 2, 30.4, 60, deg, 13)
+        _conv_case(dev, f32, ir, 2, ir, 4, 8, 32, 2, None, 60, deg, 14)
+        _conv_case(dev, f32, "8x0e+8x1o+4x2e", 2, "8x0e+8x1o+4x2e", 3, 8, 8, 1, 10.0, 64, lambda n: 12, 15)
+        _conv_case(dev, f32, "8x0e+8x1o+4x2e", 2, "8x0e+8x1o+4x2e", 1, 10, 8, 0, 10.0, 64, lambda n: 12, 16)
+        _conv_case(dev, f32, "20x0e+12x1o+5x2e+3x1e", 2, "20x0e+12x1o+5x2e+3x1e", 2, 8, 16, 3, 9.0, 100,
+                   lambda n: n % 40, 17)
+
+    _with_impl(impl, run)
+
+
+def test_conv_tc_matches_fma_bitwise_determinism(dev):
+    """the tensor-core path is deterministic run to run as well"""
+    ir = "32x0o+32x0e+16x1o+16x1e+4x2o+4x2e"
+    _with_impl("tc", lambda: _conv_case(dev, torch.float32, ir, 2, ir, 8, 8, 32, 2, 28.0, 500,
+                                        lambda n: 20 + (n % 17), 18))
