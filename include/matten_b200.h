@@ -175,7 +175,7 @@ typedef struct {
    * packed into one group as lane-phased sub-items:
    *   tc_row_wcol [tc_num_tiles*128]   : weight column of every A row (-1 = zero row)
    *   tc_sub_hdr  [tc_num_sub,8]       : {cg_type_id, cols_per_warp, first TMEM lane in the quarter,
-   *                                       tile, quarter, 0, 0, 0}
+   *                                       tile, quarter, 2*l3+1, 0, 0}  (l1,l2,l3 <= 2 only)
    *   tc_sub_slot [tc_num_sub,32,4]    : per lane {x offset, sh offset, out offset, valid}
    *   tc_q_list   [4,64], tc_q_count[4]: sub-items of every quarter, heaviest first            */
   int32_t tc_num_tiles;
@@ -193,10 +193,15 @@ typedef struct {
  *   (sum_{e: dst(e)=n} msg_e) / sqrt(avg_num_neighbors)        if num_neigh == NULL
  *   (sum ...)             / sqrt(num_neigh[n])                  otherwise (reference
  *   src/matten/nn/conv.py:116-120). Summation order is the CSR order: deterministic. */
+/* workspace (bytes) of the tcgen05 path: the hidden activations of the radial MLP as bf16 hi/mid/lo
+ * planes (192 B per edge) and 16-byte padded sh rows, both in receiver-sorted order.  0 when the plan /
+ * dtype runs on the FMA-pipe kernel, which needs none. */
+size_t mt_conv_fwd_workspace_bytes(const mt_conv_plan* plan, int dtype, int64_t N, int64_t E);
 int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* sh,
                 const void* emb, const void* const* mlp_weights, const int32_t* rowptr,
                 const int32_t* perm, const int32_t* src_sorted, double avg_num_neighbors,
-                const void* num_neigh, void* out, int64_t N, int64_t E, mt_stream stream);
+                const void* num_neigh, void* out, void* workspace, size_t workspace_bytes, int64_t N,
+                int64_t E, mt_stream stream);
 
 /* ------------------------------------------------------------------------- *
  * a8 / a11 / a13 / a14: irreps-wise linear maps.

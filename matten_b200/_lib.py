@@ -59,8 +59,9 @@ SIGNATURES = {
     "mt_gather_i64_to_i32": (_I, [_V, _V, _L, _V, _V]),
     "mt_check_sorted": (_I, [_V, _L, _V, _V]),
     "mt_species_embed": (_I, [_I, _V, _I, _V, _L, _L, _I, _I, _V, _V, _L, _V, _V, _V, _V, _V]),
+    "mt_conv_fwd_workspace_bytes": (_Z, [C.POINTER(ConvPlanStruct), _I, _L, _L]),
     "mt_conv_fwd": (_I, [C.POINTER(ConvPlanStruct), _I, _V, _V, _V, C.POINTER(_V), _V, _V, _V, _D, _V, _V,
-                         _L, _L, _V]),
+                         _V, _Z, _L, _L, _V]),
     "mt_linear_fwd": (_I, [_I, C.POINTER(LinBlockStruct), _I, _I, _I, _I, _V, _V, _V, _V, _I, _V, _L, _V]),
     "mt_gate_fwd": (_I, [_I, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _L, _V]),
     "mt_segment_reduce": (_I, [_I, _V, _V, _I, _L, _I, _V, _V]),

@@ -186,6 +186,12 @@ def generate() -> str:
     for i, (a, b, c) in enumerate(types):
         L.append(f"  X({i}, {a}, {b}, {c}) \\")
     L.append("")
+    L.append("// the same, restricted to l1, l2, l3 <= 2 (the tcgen05 convolution kernel)")
+    L.append("#define MT_FOR_EACH_CG_TYPE_L2(X) \\")
+    for i, (a, b, c) in enumerate(types):
+        if max(a, b, c) <= 2:
+            L.append(f"  X({i}, {a}, {b}, {c}) \\")
+    L.append("")
     L.append("__host__ __device__ constexpr int cg_type_id(int l1, int l2, int l3) {")
     L.append("  switch (l1 * 100 + l2 * 10 + l3) {")
     for i, (a, b, c) in enumerate(types):

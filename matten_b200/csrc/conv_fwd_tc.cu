@@ -1,21 +1,42 @@
 // Host launcher of the tcgen05 convolution forward (see conv_fwd_tc.cuh).
+#include <stdlib.h>
+
 #include "conv_fwd_tc.cuh"
 
 namespace mt {
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static bool tc_plan_qualifies(const mt_conv_plan* plan) {
+  if (plan->tc_num_tiles <= 0 || plan->tc_num_tiles > kTcMaxTiles) return false;
+  if (plan->tc_num_sub <= 0 || plan->tc_num_sub > kTcMaxSub) return false;
+  if (!plan->tc_row_wcol || !plan->tc_sub_hdr || !plan->tc_sub_slot || !plan->tc_q_list) return false;
+  if (plan->mlp_num_layers > 3) return false;  // at most two hidden layers in the preparation kernel
+  for (int i = 0; i < plan->mlp_num_layers; ++i)
+    if (plan->mlp_sizes[i] > kTcK) return false;
+  if (plan->x_dim > 65535 || plan->y_dim > 252 || (plan->x_dim & 3) != 0) return false;  // 16-byte bulk copies
+  const int y_pad = (plan->y_dim + 3) & ~3;
+  const TcSmemLayout L = tc_smem_layout(plan->tc_num_tiles, plan->x_dim, y_pad, plan->tc_num_sub);
+  return L.total + 512 <= (size_t)227 * 1024;  // dynamic + static shared memory must fit 227 KB
+}
+
+size_t conv_fwd_tc_workspace_bytes(const mt_conv_plan* plan, int64_t E) {
+  if (!tc_plan_qualifies(plan) || E <= 0) return 0;
+  const int y_pad = (plan->y_dim + 3) & ~3;
+  return align256((size_t)E * 192) + align256((size_t)E * y_pad * 4) + 256;
+}
 
 // returns MT_OK and sets *used = 1 when the tensor-core path ran; *used = 0 when the plan/shape does not
 // qualify (caller falls back to the FMA-pipe kernel)
 int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, const void* emb,
                     const void* const* mlp_weights, const int32_t* rowptr, const int32_t* perm,
-                    const int32_t* src_sorted, double avg, const void* num_neigh, void* out, int64_t N, int64_t E,
-                    cudaStream_t st, int* used) {
+                    const int32_t* src_sorted, double avg, const void* num_neigh, void* out, void* workspace,
+                    size_t workspace_bytes, int64_t N, int64_t E, cudaStream_t st, int* used) {
   *used = 0;
-  if (plan->tc_num_tiles <= 0 || plan->tc_num_tiles > kTcMaxTiles) return MT_OK;
-  if (plan->tc_num_sub <= 0 || plan->tc_num_sub > kTcMaxSub) return MT_OK;
-  if (!plan->tc_row_wcol || !plan->tc_sub_hdr || !plan->tc_sub_slot || !plan->tc_q_list) return MT_OK;
-  for (int i = 0; i < plan->mlp_num_layers; ++i)
-    if (plan->mlp_sizes[i] > kTcK) return MT_OK;
+  if (!tc_plan_qualifies(plan)) return MT_OK;
   if (E >= (int64_t)2147483647 || N >= (int64_t)2147483647) return MT_OK;
+  const size_t need = conv_fwd_tc_workspace_bytes(plan, E);
+  if (E > 0 && (workspace == nullptr || workspace_bytes < need)) return MT_OK;
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   p.x_dim = plan->x_dim;
@@ -44,17 +65,31 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
   p.out = static_cast<float*>(out);
   p.N = N;
   p.E = E;
-  p.xs_stride = p.x_dim;
-  const TcSmemLayout L = tc_smem_layout(p.num_tiles, p.xs_stride, p.y_dim);
-  if (L.total > (size_t)227 * 1024 - 256) return MT_OK;  // does not fit: fall back
+  p.y_pad = (p.y_dim + 3) & ~3;
+  {
+    // workspace: 256-byte aligned sub-buffers
+    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+    p.hplanes = reinterpret_cast<__nv_bfloat16*>(base);
+    p.ysorted = reinterpret_cast<float*>(base + align256((size_t)E * 192));
+  }
+  const char* dbg = getenv("MT_CONV_TC_DEBUG");
+  p.dbg = (dbg && *dbg) ? reinterpret_cast<long long*>(strtoull(dbg, nullptr, 10)) : nullptr;
+  const TcSmemLayout L = tc_smem_layout(p.num_tiles, p.x_dim, p.y_pad, p.num_sub);
+  if (E > 0) {
+    int64_t g = ceil_div<int64_t>(E, kPrepThreads);
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    if (g > cap) g = cap;
+    edge_prepare_kernel<<<(unsigned)g, kPrepThreads, 0, st>>>(p);
+    MT_LAUNCH_OK();
+  }
+  int64_t grid = kNumSMs;
+  if (grid > N) grid = N;
+  if (grid < 1) grid = 1;
   static thread_local size_t configured = 0;
   if (L.total > configured) {
     MT_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     configured = L.total;
   }
-  int64_t grid = kNumSMs;
-  if (grid > N) grid = N;
-  if (grid < 1) grid = 1;
   conv_fwd_tc_kernel<<<(unsigned)grid, kTcThreads, L.total, st>>>(p);
   MT_LAUNCH_OK();
   *used = 1;

@@ -234,13 +234,15 @@ def conv_fwd(handle: ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Ten
     if num_neigh is not None:
         num_neigh = _req(num_neigh, "num_neigh", x.dtype)
     out = torch.empty((N, pl.out_dim), dtype=x.dtype, device=x.device)
+    ws_bytes = lib.mt_conv_fwd_workspace_bytes(C.byref(handle.struct), _dt(x), N, E)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     if CONV_EVENTS is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         ev0.record()
     check(lib.mt_conv_fwd(C.byref(handle.struct), _dt(x), _p(x), _p(sh), _p(emb), wptrs, _p(rowptr), _p(perm),
                           _p(src_sorted), float(avg_num_neighbors) if avg_num_neighbors is not None else 0.0,
-                          _p(num_neigh), _p(out), N, E, _stream(x)))
+                          _p(num_neigh), _p(out), _p(ws), ws_bytes, N, E, _stream(x)))
     if CONV_EVENTS is not None:
         ev1.record()
         CONV_EVENTS.append(((pl.x_dim, pl.y_dim, pl.out_dim, pl.weight_numel, N, E), ev0, ev1))

@@ -111,6 +111,9 @@ class UVUPlan:
         into full groups of 32 (one sub-item, lane == row) plus a remainder that is padded to cpw = 8 or 16
         lanes and packed with other small remainders into shared groups; a packed sub-item runs on all 32
         lanes as (column, edge-phase) pairs.  Groups are spread over the 4 quarters to balance their cost."""
+        self.tc_num_tiles = 0
+        if max(max(p.l1, p.l2, p.l3) for p in self.paths) > 2:
+            return  # the tensor-core kernel instantiates the l <= 2 contractions only
         by_type = {}
         for p in self.paths:
             cols = by_type.setdefault((p.l1, p.l2, p.l3), [])
@@ -122,7 +125,8 @@ class UVUPlan:
             for c0 in range(0, len(cols), 32):
                 chunk = cols[c0:c0 + 32]
                 cpw = 32 if len(chunk) > 16 else (16 if len(chunk) > 8 else 8)
-                subs.append({"type": cg_type_id(l1, l2, l3), "cpw": cpw, "cols": chunk, "cost": base * cpw / 32.0})
+                subs.append({"type": cg_type_id(l1, l2, l3), "cpw": cpw, "cols": chunk, "cost": base * cpw / 32.0,
+                             "d3": 2 * l3 + 1})
         # pack: cpw == 32 sub-items own a group; smaller ones share groups (first fit, large first)
         groups = []  # list of list of (sub index, lane0)
         for i, sb in enumerate(subs):
@@ -158,7 +162,7 @@ class UVUPlan:
             qcost[q] += g["cost"]
             for i, lane0 in g["subs"]:
                 sb = subs[i]
-                hdr[i] = [sb["type"], sb["cpw"], lane0, t, q, 0, 0, 0]
+                hdr[i] = [sb["type"], sb["cpw"], lane0, t, q, sb["d3"], 0, 0]
                 for j, (wc, xo, yo, oo) in enumerate(sb["cols"]):
                     row_wcol[t * 128 + q * 32 + lane0 + j] = wc
                 for lane in range(32):

@@ -372,10 +372,16 @@ def test_conv_tensor_core_and_fma_paths(dev, impl):
         _conv_case(dev, f32, ir, 2, ir, 4, 8, 32, 2, None, 60, deg, 14)
         _conv_case(dev, f32, "8x0e+8x1o+4x2e", 2, "8x0e+8x1o+4x2e", 3, 8, 8, 1, 10.0, 64, lambda n: 12, 15)
         _conv_case(dev, f32, "8x0e+8x1o+4x2e", 2, "8x0e+8x1o+4x2e", 1, 10, 8, 0, 10.0, 64, lambda n: 12, 16)
-        _conv_case(dev, f32, "20x0e+12x1o+5x2e+3x1e", 2, "20x0e+12x1o+5x2e+3x1e", 2, 8, 16, 3, 9.0, 100,
+        _conv_case(dev, f32, "20x0e+12x1o+4x2e+4x1e", 2, "20x0e+12x1o+4x2e+4x1e", 2, 8, 16, 2, 9.0, 100,
                    lambda n: n % 40, 17)
 
     _with_impl(impl, run)
+    # row length not a multiple of 4 floats (no 16-byte bulk copies): automatic fallback to the FMA kernel
+    _with_impl("auto", lambda: _conv_case(dev, f32, "20x0e+12x1o+5x2e+3x1e", 2, "20x0e+12x1o+5x2e+3x1e", 2, 8, 16, 2,
+                                          9.0, 60, lambda n: n % 30, 20))
+    # three hidden layers: the tensor-core path keeps at most two in registers -> automatic fallback
+    _with_impl("auto", lambda: _conv_case(dev, f32, "20x0e+12x1o+5x2e", 2, "20x0e+12x1o+5x2e", 2, 8, 16, 3, 9.0,
+                                          50, lambda n: n % 20, 19))
 
 
 def test_conv_tc_matches_fma_bitwise_determinism(dev):
