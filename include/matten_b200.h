@@ -185,6 +185,16 @@ typedef struct {
   const int32_t* tc_sub_slot; /* device */
   const int32_t* tc_q_list;   /* device */
   int32_t tc_q_count[4];
+  /* Tables of the backward pass (mt_conv_bwd), organised by INPUT channel so that the gradient of a
+   * gathered x row is a register sum in fixed path order; bw_num_items == 0: forward-only plan.
+   *   bw_item_hdr [bw_num_items,4]   : {l1, cols_per_warp, first path, path count}
+   *   bw_lane_tab [bw_num_items,32,2]: per lane {u (-1 = idle lane), offset of x[u,:] in the x row}
+   *   bw_path_tab [bw_num_paths,4]   : {cg_type_id, weight column of u = 0, sh offset, out offset of u = 0} */
+  int32_t bw_num_items;
+  int32_t bw_num_paths;
+  const int32_t* bw_item_hdr; /* device */
+  const int32_t* bw_lane_tab; /* device */
+  const int32_t* bw_path_tab; /* device */
 } mt_conv_plan;
 
 /* x [N,x_dim]; sh [E,y_dim], emb [E,mlp_sizes[0]] in ORIGINAL edge order;
@@ -202,6 +212,26 @@ int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* 
                 const int32_t* perm, const int32_t* src_sorted, double avg_num_neighbors,
                 const void* num_neigh, void* out, void* workspace, size_t workspace_bytes, int64_t N,
                 int64_t E, mt_stream stream);
+
+/* Backward of mt_conv_fwd (what autograd does through weight_nn + tp + scatter + div in the reference,
+ * src/matten/nn/conv.py:111-120).  Inputs as in mt_conv_fwd plus
+ *   grad_out [N,out_dim]            : dL/d out
+ *   sender_ptr [N+1], sender_perm [E]: CSR over the SENDERS of the receiver-sorted edge list
+ *                                     (mt_csr_by_key on src_sorted): sender_perm[i] is a position in the
+ *                                     receiver-sorted list
+ * Outputs (either group may be NULL to skip it):
+ *   grad_x [N,x_dim]                : dL/dx, summed per sender in sender-CSR order (deterministic)
+ *   grad_mlp_weights[i]             : dL/d weights[i], same shapes as mlp_weights[i]; per-CTA partial sums
+ *                                     reduced in a fixed order (deterministic for a fixed N, E)
+ * workspace: mt_conv_bwd_workspace_bytes bytes (hidden pre-activations, per-edge dw / dx scratch, partial
+ * weight gradients). */
+size_t mt_conv_bwd_workspace_bytes(const mt_conv_plan* plan, int dtype, int64_t N, int64_t E);
+int mt_conv_bwd(const mt_conv_plan* plan, int dtype, const void* x, const void* sh, const void* emb,
+                const void* const* mlp_weights, const int32_t* rowptr, const int32_t* perm,
+                const int32_t* src_sorted, const int32_t* sender_ptr, const int32_t* sender_perm,
+                double avg_num_neighbors, const void* num_neigh, const void* grad_out, void* grad_x,
+                void* const* grad_mlp_weights, void* workspace, size_t workspace_bytes, int64_t N, int64_t E,
+                mt_stream stream);
 
 /* ------------------------------------------------------------------------- *
  * a8 / a11 / a13 / a14: irreps-wise linear maps.
@@ -227,6 +257,20 @@ int mt_linear_fwd(int dtype, const mt_lin_block* blocks, int num_blocks, int in_
                   const int32_t* species_perm, const int32_t* species_ptr, int accumulate,
                   void* out, int64_t N, mt_stream stream);
 
+/* Backward of mt_linear_fwd.
+ *   grad_x [N,in_dim]  (may be NULL): scale * sum_w weight[(u*S+s_n)*mul_out + w] * grad_out[n, w, m];
+ *                      elements of x that feed no block get 0.  accumulate_x != 0 adds into grad_x.
+ *   grad_w [weight numel] (may be NULL): scale * sum_{n of species s} sum_m x[n,u,m] * grad_out[n,w,m];
+ *                      node range split over CTAs, partials reduced in fixed order (deterministic).
+ *                      accumulate_w != 0 adds into grad_w (gradient accumulation).
+ * workspace: mt_linear_bwd_workspace_bytes(weight_numel) bytes (0 when grad_w is NULL). */
+size_t mt_linear_bwd_workspace_bytes(int dtype, int64_t weight_numel);
+int mt_linear_bwd(int dtype, const mt_lin_block* blocks, int num_blocks, int in_dim, int out_dim,
+                  int num_species, int64_t weight_numel, const void* x, const void* weight,
+                  const void* grad_out, const int32_t* species_perm, const int32_t* species_ptr,
+                  void* grad_x, int accumulate_x, void* grad_w, int accumulate_w, void* workspace,
+                  size_t workspace_bytes, int64_t N, mt_stream stream);
+
 /* ------------------------------------------------------------------------- *
  * a9 + a10: e3nn.nn.Gate followed by e3nn.nn.BatchNorm in eval mode (reference
  * src/matten/nn/utils.py:134-140, 418, applied at src/matten/nn/conv.py:209-211).
@@ -240,6 +284,50 @@ int mt_gate_fwd(int dtype, const void* x, int in_dim, int out_dim, const int32_t
                 const int32_t* gate_idx, const int32_t* act_id, const void* act_cst,
                 const void* affine_a, const void* affine_b, void* out, int64_t N,
                 mt_stream stream);
+
+/* Backward of mt_gate_fwd w.r.t. x (the affine is treated as constant).  inv_first / inv_count
+ * [in_dim] invert the element tables: input i feeds outputs inv_first[i] .. + inv_count[i] - 1 (one
+ * output for a scalar or gated element, the 2l+1 gated outputs for a gate; count 0: unused input). */
+int mt_gate_bwd(int dtype, const void* x, const void* grad_out, int in_dim, int out_dim,
+                const int32_t* src_idx, const int32_t* gate_idx, const int32_t* act_id, const void* act_cst,
+                const void* affine_a, const int32_t* inv_first, const int32_t* inv_count, void* grad_x,
+                int64_t N, mt_stream stream);
+
+/* Column reductions over the node axis (training-mode e3nn BatchNorm statistics and their backward,
+ * reference src/matten/nn/utils.py:418; bias gradients):
+ *   out[j] = sum_n (a[n,j] - shift_a[j]) * (b ? (b[n,j] - shift_b[j]) : 1)      j < dim
+ * a, b [N,dim] (b may be NULL or equal to a); shift_* [dim] may be NULL (0).  Two-stage, fixed order.
+ * workspace: mt_col_reduce_workspace_bytes(dtype, dim) bytes. */
+size_t mt_col_reduce_workspace_bytes(int dtype, int dim);
+int mt_col_reduce(int dtype, const void* a, const void* shift_a, const void* b, const void* shift_b,
+                  int64_t N, int dim, void* out, void* workspace, size_t workspace_bytes, mt_stream stream);
+
+/* out[n,j] = ca[j] * a[n,j] + (b ? cb[j] * b[n,j] : 0) + cc[j]   (BatchNorm apply and its backward). */
+int mt_affine2(int dtype, const void* a, const void* ca, const void* b, const void* cb, const void* cc,
+               void* out, int64_t N, int dim, mt_stream stream);
+
+/* Backward of mt_segment_reduce for mode 0 (sum) / 1 (mean): grad_x[n,:] = grad_out[b(n),:] (/ count). */
+int mt_segment_reduce_bwd(int dtype, const void* grad_out, const int32_t* ptr, int dim, int64_t B, int64_t N,
+                          int mode, void* grad_x, mt_stream stream);
+
+/* out[s,:] = sum_{i in [ptr[s], ptr[s+1])} x[perm ? perm[i] : i, :], fixed order; num_rows = ptr[num_segments]
+ * (a block-level sum is used when segments are long).  Used for the species-embedding gradient (backward of mt_species_embed: dW[:,s]) and for the
+ * per-sender reduction of the conv backward. */
+int mt_segment_sum_gather(int dtype, const void* x, const int32_t* perm, const int32_t* ptr, int dim,
+                          int64_t num_segments, int64_t num_rows, void* out, mt_stream stream);
+
+/* a17: loss and optimiser (reference src/matten/model/model.py:234-274: MSE with mean reduction;
+ * scripts/configs/materials_tensor.yaml:103-107: torch.optim.Adam(lr, weight_decay), L2 form).
+ *   mt_mse_loss: loss[0] = mean((pred - target)^2), grad[i] = 2 (pred - target) / n * grad_scale
+ *                (either output may be NULL); single CTA, fixed order.
+ *   mt_adam_step: p, g, m, v flat [n]; torch.optim.Adam semantics (amsgrad off):
+ *                g' = g * grad_scale + wd * p; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2;
+ *                p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps) */
+int mt_mse_loss(int dtype, const void* pred, const void* target, int64_t n, double grad_scale, void* loss,
+                void* grad, mt_stream stream);
+int mt_adam_step(int dtype, void* p, const void* g, void* m, void* v, int64_t n, double lr, double beta1,
+                 double beta2, double eps, double weight_decay, double grad_scale, int64_t step,
+                 mt_stream stream);
 
 /* a12: torch_scatter.scatter(x, batch, reduce) over a SORTED batch vector (reference
  * src/matten/nn/nodewise.py:142-148).  ptr [B+1] from mt_csr_by_key on batch.

@@ -32,6 +32,8 @@ class ConvPlanStruct(C.Structure):
         ("tc_num_tiles", C.c_int32), ("tc_num_sub", C.c_int32),
         ("tc_row_wcol", C.c_void_p), ("tc_sub_hdr", C.c_void_p), ("tc_sub_slot", C.c_void_p),
         ("tc_q_list", C.c_void_p), ("tc_q_count", C.c_int32 * 4),
+        ("bw_num_items", C.c_int32), ("bw_num_paths", C.c_int32),
+        ("bw_item_hdr", C.c_void_p), ("bw_lane_tab", C.c_void_p), ("bw_path_tab", C.c_void_p),
     ]
 
 
@@ -62,6 +64,20 @@ SIGNATURES = {
     "mt_conv_fwd_workspace_bytes": (_Z, [C.POINTER(ConvPlanStruct), _I, _L, _L]),
     "mt_conv_fwd": (_I, [C.POINTER(ConvPlanStruct), _I, _V, _V, _V, C.POINTER(_V), _V, _V, _V, _D, _V, _V,
                          _V, _Z, _L, _L, _V]),
+    "mt_conv_bwd_workspace_bytes": (_Z, [C.POINTER(ConvPlanStruct), _I, _L, _L]),
+    "mt_conv_bwd": (_I, [C.POINTER(ConvPlanStruct), _I, _V, _V, _V, C.POINTER(_V), _V, _V, _V, _V, _V, _D, _V, _V, _V,
+                         C.POINTER(_V), _V, _Z, _L, _L, _V]),
+    "mt_linear_bwd_workspace_bytes": (_Z, [_I, _L]),
+    "mt_linear_bwd": (_I, [_I, C.POINTER(LinBlockStruct), _I, _I, _I, _I, _L, _V, _V, _V, _V, _V, _V, _I, _V, _I, _V,
+                           _Z, _L, _V]),
+    "mt_gate_bwd": (_I, [_I, _V, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _V, _L, _V]),
+    "mt_col_reduce_workspace_bytes": (_Z, [_I, _I]),
+    "mt_col_reduce": (_I, [_I, _V, _V, _V, _V, _L, _I, _V, _V, _Z, _V]),
+    "mt_affine2": (_I, [_I, _V, _V, _V, _V, _V, _V, _L, _I, _V]),
+    "mt_segment_reduce_bwd": (_I, [_I, _V, _V, _I, _L, _L, _I, _V, _V]),
+    "mt_segment_sum_gather": (_I, [_I, _V, _V, _V, _I, _L, _L, _V, _V]),
+    "mt_mse_loss": (_I, [_I, _V, _V, _L, _D, _V, _V, _V]),
+    "mt_adam_step": (_I, [_I, _V, _V, _V, _V, _L, _D, _D, _D, _D, _D, _D, _L, _V]),
     "mt_linear_fwd": (_I, [_I, C.POINTER(LinBlockStruct), _I, _I, _I, _I, _V, _V, _V, _V, _I, _V, _L, _V]),
     "mt_gate_fwd": (_I, [_I, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _L, _V]),
     "mt_segment_reduce": (_I, [_I, _V, _V, _I, _L, _I, _V, _V]),

@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
 ]
 
-PLAIN_SOURCES = ["api.cu", "graph_ops.cu", "node_ops.cu", "conv.cu", "conv_fwd_tc.cu"]
+PLAIN_SOURCES = ["api.cu", "graph_ops.cu", "node_ops.cu", "train_ops.cu", "conv.cu", "conv_fwd_tc.cu", "conv_bwd.cu"]
 CONV_INST = [(t, hp) for t in ("float", "double") for hp in (8, 16, 32, 64)]
 
 

@@ -1,0 +1,448 @@
+// Backward of the fused convolution (mt_conv_bwd, include/matten_b200.h).
+//
+// What autograd does in the reference through
+//   src/matten/nn/utils.py:260   weight = weight_nn(edge_embedding)
+//   src/matten/nn/utils.py:263   msg = tp(x[src], sh, weight)
+//   src/matten/nn/conv.py:114    scatter(msg, dst)        conv.py:116  .div(sqrt(avg_num_neighbors))
+// restated as five kernels, none of which materialises the messages:
+//   K0 edge_hidden_kernel      pre-activations z_l of the hidden MLP layers per edge (receiver-sorted order)
+//   K1 conv_bwd_kernel         CTA <-> tile of receiver nodes, edges staged in shared memory in chunks:
+//                              (A) per-edge weights w[e,:] = a_last[e,:] @ W_last/sqrt(H) into shared memory,
+//                              (B) warp <-> (32 input channels of one irrep) x node, lane <-> channel u: walks
+//                                  the node's edges and, per edge, every path reading the channel:
+//                                  dw[e,c] = <CG(x_u, Y), g_u>/den -> DW scratch; dx_u += w[e,c]/den * CG^T(Y, g_u)
+//                                  -> DXE scratch.  Register sums in fixed path order: deterministic.
+//   K2 mlp_bwd_last_kernel     dW_last = a_last^T DW / sqrt(H) (per-CTA partials) and da_last = DW W_last^T/sqrt(H)
+//   K3 mlp_bwd_hidden_kernel   the hidden layers: dz = da * act'(z) * cst, dW_l partials, da_l
+//   K4 reduce_partials_kernel  fixed-order sum of the per-CTA partial weight gradients
+// and the per-sender sum of DXE rows over the sender CSR (segment_sum_gather, node_ops.cu).
+#pragma once
+#include "common.cuh"
+#include "generated/cg_gen.cuh"
+
+namespace mt {
+
+constexpr int kBwdMaxH = 64;     // largest MLP layer input/hidden size the backward supports
+constexpr int kBwdET = 8;        // edges per register pass of phase A (chunk_edges is a multiple of it)
+constexpr int kLastEB = 64;      // edges per chunk of K2
+constexpr int kLastCW = 128;     // weight columns per CTA column group of K2
+constexpr int kHidEB = 64;       // edges per chunk of K0 / K3
+
+struct ConvBwdParams {
+  int x_dim, y_dim, out_dim, Wn;
+  int num_items, num_paths;
+  const int32_t* item_hdr;  // [num_items][4]
+  const int32_t* lane_tab;  // [num_items][32][2]
+  const int32_t* path_tab;  // [num_paths][4]
+  int nl;
+  int sizes[MT_MAX_MLP_LAYERS + 1];
+  int act;
+  double act_cst;
+  const void* w[MT_MAX_MLP_LAYERS];
+  void* z[MT_MAX_MLP_LAYERS];  // z[l] [E][sizes[l+1]] for l < nl-1 (workspace)
+  const void* x;
+  const void* sh;
+  const void* emb;
+  const int32_t* rowptr;
+  const int32_t* perm;
+  const int32_t* src;
+  double avg;
+  const void* num_neigh;
+  const void* g;   // grad_out [N][out_dim]
+  void* DW;        // [E][Wn]
+  void* DXE;       // [E][x_dim]
+  void* DHP;       // [ncg][E][H]
+  void* PARTL;     // [grid2][H][Wn]
+  void* PARTH;     // [grid3][hidden numel]
+  int64_t N, E;
+  int tile_nodes, chunk_edges, xs_stride, hs_stride, wt_stride;
+  int ncg, grid2, grid3, hid_numel;
+};
+
+// last-layer input a_{nl-1}[e][k]: act(z_{nl-2}) * cst, or the embedding itself for a single-layer MLP
+template <typename T>
+__device__ __forceinline__ T last_input(const ConvBwdParams& p, int64_t e, int k) {
+  if (p.nl == 1) return static_cast<const T*>(p.emb)[(size_t)p.perm[e] * p.sizes[0] + k];
+  const T z = static_cast<const T*>(p.z[p.nl - 2])[(size_t)e * p.sizes[p.nl - 1] + k];
+  return apply_act<T>(p.act, z) * T(p.act_cst);
+}
+
+// ---------------------------------------------------------------------------------------------- K0
+template <typename T>
+__global__ void __launch_bounds__(256) edge_hidden_kernel(const ConvBwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* A = reinterpret_cast<T*>(smem_raw);               // [kHidEB][kBwdMaxH + 1]
+  T* Wl = A + (size_t)kHidEB * (kBwdMaxH + 1);         // [<=64][<=64] of the current layer, pre-scaled
+  const int tid = threadIdx.x;
+  const int64_t nchunks = ceil_div<int64_t>(p.E, kHidEB);
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int64_t e0 = ch * kHidEB;
+    const int ne = (int)imin64(kHidEB, p.E - e0);
+    const int in0 = p.sizes[0];
+    __syncthreads();
+    for (int t = tid; t < ne * in0; t += blockDim.x) {
+      const int el = t / in0, k = t - el * in0;
+      A[el * (kBwdMaxH + 1) + k] = static_cast<const T*>(p.emb)[(size_t)p.perm[e0 + el] * in0 + k];
+    }
+    for (int l = 0; l + 1 < p.nl; ++l) {
+      const int fi = p.sizes[l], fo = p.sizes[l + 1];
+      const T s = T(1) / sqrt(T(fi));
+      const T* __restrict__ Wg = static_cast<const T*>(p.w[l]);
+      for (int t = tid; t < fi * fo; t += blockDim.x) Wl[t] = Wg[t] * s;
+      __syncthreads();
+      T* Z = static_cast<T*>(p.z[l]);
+      for (int t = tid; t < ne * fo; t += blockDim.x) {
+        const int el = t / fo, j = t - el * fo;
+        const T* ar = A + el * (kBwdMaxH + 1);
+        T acc = T(0);
+        for (int k = 0; k < fi; ++k) acc = fma(ar[k], Wl[k * fo + j], acc);
+        Z[(size_t)(e0 + el) * fo + j] = acc;
+      }
+      __syncthreads();
+      // every thread re-reads the entries it wrote itself (same t mapping): no fence needed
+      for (int t = tid; t < ne * fo; t += blockDim.x) {
+        const int el = t / fo, j = t - el * fo;
+        A[el * (kBwdMaxH + 1) + j] = apply_act<T>(p.act, Z[(size_t)(e0 + el) * fo + j]) * T(p.act_cst);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K1
+template <typename T, int L1>
+__device__ __forceinline__ void bwd_unit(const ConvBwdParams& p, const int4* __restrict__ spath, int pfirst, int pcount,
+                                         int u, int xoff, const T* __restrict__ xs, const T* __restrict__ ys,
+                                         const T* __restrict__ wt, const T* __restrict__ gs, int el0, int el1,
+                                         int phase, int nphase, int c0, T inv_den) {
+  constexpr int D1 = 2 * L1 + 1;
+  T* __restrict__ DW = static_cast<T*>(p.DW);
+  T* __restrict__ DXE = static_cast<T*>(p.DXE);
+  if (u < 0) return;
+  for (int el = el0 + phase; el < el1; el += nphase) {
+    T xv[D1], dxv[D1];
+    const T* xr = xs + (size_t)el * p.xs_stride + xoff;
+#pragma unroll
+    for (int m = 0; m < D1; ++m) { xv[m] = xr[m]; dxv[m] = T(0); }
+    const T* wrow = wt + (size_t)el * p.wt_stride;
+    const T* yrow = ys + (size_t)el * p.y_dim;
+    T* dwrow = DW + (size_t)(c0 + el) * p.Wn;
+    for (int pk = 0; pk < pcount; ++pk) {
+      const int4 pt = spath[pfirst + pk];  // {type, weight column of u = 0, sh offset, out offset of u = 0}
+      const int c = pt.y + u;
+      const T w = wrow[c] * inv_den;
+      switch (pt.x) {
+#define MT_BWD_CASE(ID, A, B, C)                                   \
+  case ID:                                                         \
+    if constexpr (A == L1) {                                       \
+      constexpr int D2 = 2 * B + 1, D3 = 2 * C + 1;                \
+      T yv[D2], gv[D3];                                            \
+      _Pragma("unroll") for (int m = 0; m < D2; ++m) yv[m] = yrow[pt.z + m]; \
+      const T* gr = gs + pt.w + u * D3;                            \
+      _Pragma("unroll") for (int m = 0; m < D3; ++m) gv[m] = gr[m]; \
+      dwrow[c] = CG<A, B, C>::template dot<T>(xv, yv, gv) * inv_den; \
+      CG<A, B, C>::template bwd_x<T>(yv, gv, w, dxv);              \
+    }                                                              \
+    break;
+        MT_FOR_EACH_CG_TYPE(MT_BWD_CASE)
+#undef MT_BWD_CASE
+        default: break;
+      }
+    }
+    T* dxr = DXE + (size_t)(c0 + el) * p.x_dim + xoff;
+#pragma unroll
+    for (int m = 0; m < D1; ++m) dxr[m] = dxv[m];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) conv_bwd_kernel(const ConvBwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int EC = p.chunk_edges;
+  int4* spath = reinterpret_cast<int4*>(smem_raw);     // [num_paths]
+  T* hs = reinterpret_cast<T*>(spath + p.num_paths);   // [EC][hs_stride]  (hs_stride is a multiple of 4)
+  T* xs = hs + (size_t)EC * p.hs_stride;               // [EC][xs_stride]
+  T* ys = xs + (size_t)EC * p.xs_stride;               // [EC][y_dim]
+  T* wt = ys + (size_t)EC * p.y_dim;                   // [EC][wt_stride]
+  T* gs = wt + (size_t)EC * p.wt_stride;               // [tile_nodes][out_dim]
+  __shared__ int s_counter;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const T* __restrict__ X = static_cast<const T*>(p.x);
+  const T* __restrict__ SH = static_cast<const T*>(p.sh);
+  const T* __restrict__ G = static_cast<const T*>(p.g);
+  const int H = p.sizes[p.nl - 1];
+  const T* __restrict__ Wlast = static_cast<const T*>(p.w[p.nl - 1]);
+  const int Wn = p.Wn;
+  const T inv_sqrt_h = T(1) / sqrt(T(H));
+
+  for (int t = tid; t < p.num_paths; t += blockDim.x) spath[t] = reinterpret_cast<const int4*>(p.path_tab)[t];
+  __syncthreads();
+
+  const int64_t num_tiles = ceil_div<int64_t>(p.N, p.tile_nodes);
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t n0 = tile * p.tile_nodes;
+    const int tn = (int)imin64(p.tile_nodes, p.N - n0);
+    const int e_begin = p.rowptr[n0], e_end = p.rowptr[n0 + tn];
+    if (e_begin == e_end) continue;
+    __syncthreads();
+    // grad_out rows of the tile's nodes
+    for (int t = tid; t < tn * p.out_dim; t += blockDim.x) gs[t] = G[(size_t)n0 * p.out_dim + t];
+    for (int c0 = e_begin; c0 < e_end; c0 += EC) {
+      const int c1 = min(c0 + EC, e_end);
+      const int ne = c1 - c0;
+      __syncthreads();
+      // ------------------------------------------------------------ staging
+      for (int el = warp; el < ne; el += nwarps) {
+        const T* xr = X + (size_t)p.src[c0 + el] * p.x_dim;
+        T* xd = xs + (size_t)el * p.xs_stride;
+        for (int j = lane; j < p.x_dim; j += 32) xd[j] = xr[j];
+      }
+      for (int t = tid; t < ne * p.y_dim; t += blockDim.x) {
+        const int el = t / p.y_dim, j = t - el * p.y_dim;
+        ys[t] = SH[(size_t)p.perm[c0 + el] * p.y_dim + j];
+      }
+      for (int t = tid; t < EC * p.hs_stride; t += blockDim.x) {
+        const int el = t / p.hs_stride, k = t - el * p.hs_stride;
+        hs[t] = (el < ne && k < H) ? last_input<T>(p, (int64_t)c0 + el, k) * inv_sqrt_h : T(0);
+      }
+      if (tid == 0) s_counter = 0;
+      __syncthreads();
+      // ------------------------------------------------------------ (A) per-edge weights into shared memory
+      for (int ep = 0; ep < ne; ep += kBwdET) {
+        for (int c = tid; c < Wn; c += blockDim.x) {
+          T acc[kBwdET];
+#pragma unroll
+          for (int i = 0; i < kBwdET; ++i) acc[i] = T(0);
+          for (int k = 0; k < H; k += 4) {
+            T wv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) wv[q] = (k + q < H) ? Wlast[(size_t)(k + q) * Wn + c] : T(0);
+#pragma unroll
+            for (int i = 0; i < kBwdET; ++i) {
+              const T* hr = hs + (size_t)(ep + i) * p.hs_stride + k;  // rows beyond ne are zero
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[i] = fma(hr[q], wv[q], acc[i]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kBwdET; ++i)
+            if (ep + i < ne) wt[(size_t)(ep + i) * p.wt_stride + c] = acc[i];
+        }
+      }
+      __syncthreads();
+      // ------------------------------------------------------------ (B) units
+      const int num_units = p.num_items * tn;
+      while (true) {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(&s_counter, 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= num_units) break;
+        const int item = unit / tn;
+        const int nl_ = unit - item * tn;
+        const int64_t n = n0 + nl_;
+        const int4 hdr = reinterpret_cast<const int4*>(p.item_hdr)[item];  // {l1, cpw, first path, count}
+        const int2 ls = reinterpret_cast<const int2*>(p.lane_tab)[item * 32 + lane];
+        const int cpw = hdr.y;
+        const int phase = lane / cpw, nphase = 32 / cpw;
+        const int r0 = p.rowptr[n], r1 = p.rowptr[n + 1];
+        const int lo = max(r0, c0), hi = min(r1, c1);
+        if (lo >= hi) continue;
+        const T den = p.num_neigh ? sqrt(static_cast<const T*>(p.num_neigh)[n]) : sqrt(T(p.avg));
+        const T inv_den = T(1) / den;
+        const T* gn = gs + (size_t)nl_ * p.out_dim;
+        switch (hdr.x) {
+          case 0: bwd_unit<T, 0>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gn, lo - c0, hi - c0, phase, nphase, c0, inv_den); break;
+          case 1: bwd_unit<T, 1>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gn, lo - c0, hi - c0, phase, nphase, c0, inv_den); break;
+          case 2: bwd_unit<T, 2>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gn, lo - c0, hi - c0, phase, nphase, c0, inv_den); break;
+          case 3: bwd_unit<T, 3>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gn, lo - c0, hi - c0, phase, nphase, c0, inv_den); break;
+          case 4: bwd_unit<T, 4>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gn, lo - c0, hi - c0, phase, nphase, c0, inv_den); break;
+          default: break;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K2
+// grid (grid2, ncg): CTA (bx, cg) walks edge chunks bx, bx + grid2, ... for the weight columns of group cg.
+template <typename T, int HP>
+__global__ void __launch_bounds__(256) mlp_bwd_last_kernel(const ConvBwdParams p) {
+  constexpr int KP = HP / 8 > 0 ? HP / 8 : 1;  // k per thread of the dW tile (k = tk + 8 i)
+  constexpr int KD = HP / 4;                   // k per thread of the dH tile
+  constexpr int DS = kLastCW + 4;              // row stride of the dw tile
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* dws = reinterpret_cast<T*>(smem_raw);             // [kLastEB][DS]
+  T* hs2 = dws + (size_t)kLastEB * DS;                 // [kLastEB][HP]
+  T* WlT = hs2 + (size_t)kLastEB * HP;                 // [kLastCW][HP]  (pre-scaled by 1/sqrt(H))
+  const int tid = threadIdx.x;
+  const int H = p.sizes[p.nl - 1], Wn = p.Wn;
+  const int cg = blockIdx.y;
+  const int cbase = cg * kLastCW;
+  const int ncol = min(kLastCW, Wn - cbase);
+  const T inv_sqrt_h = T(1) / sqrt(T(H));
+  const T* __restrict__ Wlast = static_cast<const T*>(p.w[p.nl - 1]);
+  const T* __restrict__ DW = static_cast<const T*>(p.DW);
+  for (int t = tid; t < kLastCW * HP; t += blockDim.x) {
+    const int c = t / HP, k = t - c * HP;
+    WlT[t] = (c < ncol && k < H) ? Wlast[(size_t)k * Wn + cbase + c] * inv_sqrt_h : T(0);
+  }
+  const int tc = tid & 31, tk = tid >> 5;   // dW tile: columns 4 tc .. 4 tc + 3, k = tk + 8 i
+  const int te = tid >> 2, kq = tid & 3;    // dH tile: edge te, k = kq * KD .. + KD - 1
+  T accw[KP][4];
+#pragma unroll
+  for (int i = 0; i < KP; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) accw[i][j] = T(0);
+  const int64_t nchunks = ceil_div<int64_t>(p.E, kLastEB);
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int64_t e0 = ch * kLastEB;
+    const int ne = (int)imin64(kLastEB, p.E - e0);
+    __syncthreads();
+    for (int t = tid; t < kLastEB * kLastCW; t += blockDim.x) {
+      const int el = t / kLastCW, c = t - el * kLastCW;
+      dws[el * DS + c] = (el < ne && c < ncol) ? DW[(size_t)(e0 + el) * Wn + cbase + c] : T(0);
+    }
+    for (int t = tid; t < kLastEB * HP; t += blockDim.x) {
+      const int el = t / HP, k = t - el * HP;
+      hs2[t] = (el < ne && k < H) ? last_input<T>(p, e0 + el, k) : T(0);
+    }
+    __syncthreads();
+    // dW_last[k][c] += sum_e a[e][k] dw[e][c]
+    if (tk < HP) {
+      for (int el = 0; el < kLastEB; ++el) {
+        const T* dr = dws + el * DS + tc * 4;
+        const T d0 = dr[0], d1 = dr[1], d2 = dr[2], d3 = dr[3];
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+          const T hv = hs2[el * HP + tk + 8 * i];
+          accw[i][0] = fma(hv, d0, accw[i][0]);
+          accw[i][1] = fma(hv, d1, accw[i][1]);
+          accw[i][2] = fma(hv, d2, accw[i][2]);
+          accw[i][3] = fma(hv, d3, accw[i][3]);
+        }
+      }
+    }
+    // dH[e][k] (this column group) = sum_c dw[e][c] W[k][c] / sqrt(H)
+    {
+      T acch[KD];
+#pragma unroll
+      for (int i = 0; i < KD; ++i) acch[i] = T(0);
+      const T* dr = dws + te * DS;
+      for (int c = 0; c < kLastCW; ++c) {
+        const T dv = dr[c];
+        const T* wr = WlT + c * HP + kq * KD;
+#pragma unroll
+        for (int i = 0; i < KD; ++i) acch[i] = fma(dv, wr[i], acch[i]);
+      }
+      if (te < ne) {
+        T* dh = static_cast<T*>(p.DHP) + ((size_t)cg * p.E + (e0 + te)) * H;
+#pragma unroll
+        for (int i = 0; i < KD; ++i)
+          if (kq * KD + i < H) dh[kq * KD + i] = acch[i];
+      }
+    }
+  }
+  // partial dW_last of this CTA: PARTL[bx][k][c]
+  T* part = static_cast<T*>(p.PARTL) + (size_t)blockIdx.x * H * Wn;
+#pragma unroll
+  for (int i = 0; i < KP; ++i) {
+    const int k = tk + 8 * i;
+    if (k < H) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = tc * 4 + j;
+        if (c < ncol) part[(size_t)k * Wn + cbase + c] = accw[i][j];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K3
+template <typename T>
+__global__ void __launch_bounds__(256) mlp_bwd_hidden_kernel(const ConvBwdParams p) {
+  constexpr int RS = kBwdMaxH + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* DA = reinterpret_cast<T*>(smem_raw);   // [kHidEB][RS]  gradient w.r.t. the layer's output activation
+  T* DZ = DA + (size_t)kHidEB * RS;         // [kHidEB][RS]
+  T* A = DZ + (size_t)kHidEB * RS;          // [kHidEB][RS]  the layer's input activation
+  T* Wl = A + (size_t)kHidEB * RS;          // [<=64*64] current layer, pre-scaled
+  T* accW = Wl + (size_t)kBwdMaxH * kBwdMaxH;  // [hid_numel] running partial sums of this CTA
+  const int tid = threadIdx.x;
+  for (int t = tid; t < p.hid_numel; t += blockDim.x) accW[t] = T(0);
+  const int H = p.sizes[p.nl - 1];
+  const int64_t nchunks = ceil_div<int64_t>(p.E, kHidEB);
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int64_t e0 = ch * kHidEB;
+    const int ne = (int)imin64(kHidEB, p.E - e0);
+    __syncthreads();
+    // da_{nl-1}: fixed-order sum of the column-group partials of K2
+    for (int t = tid; t < kHidEB * H; t += blockDim.x) {
+      const int el = t / H, k = t - el * H;
+      T s = T(0);
+      if (el < ne)
+        for (int cg = 0; cg < p.ncg; ++cg) s += static_cast<const T*>(p.DHP)[((size_t)cg * p.E + (e0 + el)) * H + k];
+      DA[el * RS + k] = s;
+    }
+    int woff = p.hid_numel;
+    for (int l = p.nl - 2; l >= 0; --l) {
+      const int fi = p.sizes[l], fo = p.sizes[l + 1];
+      woff -= fi * fo;
+      const T s = T(1) / sqrt(T(fi));
+      const T* __restrict__ Wg = static_cast<const T*>(p.w[l]);
+      __syncthreads();
+      for (int t = tid; t < fi * fo; t += blockDim.x) Wl[t] = Wg[t] * s;
+      const T* Z = static_cast<const T*>(p.z[l]);
+      for (int t = tid; t < kHidEB * fo; t += blockDim.x) {
+        const int el = t / fo, j = t - el * fo;
+        T v = T(0);
+        if (el < ne) v = DA[el * RS + j] * apply_act_grad<T>(p.act, Z[(size_t)(e0 + el) * fo + j]) * T(p.act_cst);
+        DZ[el * RS + j] = v;
+      }
+      for (int t = tid; t < kHidEB * fi; t += blockDim.x) {
+        const int el = t / fi, k = t - el * fi;
+        T v = T(0);
+        if (el < ne) {
+          if (l == 0) v = static_cast<const T*>(p.emb)[(size_t)p.perm[e0 + el] * fi + k];
+          else v = apply_act<T>(p.act, static_cast<const T*>(p.z[l - 1])[(size_t)(e0 + el) * fi + k]) * T(p.act_cst);
+        }
+        A[el * RS + k] = v;
+      }
+      __syncthreads();
+      // dW_l[k][j] += sum_e A[e][k] DZ[e][j]   (scaled by 1/sqrt(fi) in the final reduction)
+      for (int t = tid; t < fi * fo; t += blockDim.x) {
+        const int k = t / fo, j = t - k * fo;
+        T acc = T(0);
+        for (int el = 0; el < kHidEB; ++el) acc = fma(A[el * RS + k], DZ[el * RS + j], acc);
+        accW[woff + t] += acc;
+      }
+      __syncthreads();
+      if (l > 0) {
+        // da_l[e][k] = sum_j DZ[e][j] W_l[k][j] / sqrt(fi)
+        for (int t = tid; t < kHidEB * fi; t += blockDim.x) {
+          const int el = t / fi, k = t - el * fi;
+          T acc = T(0);
+          for (int j = 0; j < fo; ++j) acc = fma(DZ[el * RS + j], Wl[k * fo + j], acc);
+          DA[el * RS + k] = acc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  T* part = static_cast<T*>(p.PARTH) + (size_t)blockIdx.x * p.hid_numel;
+  for (int t = tid; t < p.hid_numel; t += blockDim.x) part[t] = accW[t];
+}
+
+// ---------------------------------------------------------------------------------------------- K4
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const T* __restrict__ part, int64_t stride, int nparts,
+                                                              int64_t off, int64_t count, T scale,
+                                                              T* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  T s = T(0);
+  for (int b = 0; b < nparts; ++b) s += part[(size_t)b * stride + off + i];
+  out[i] = s * scale;
+}
+
+}  // namespace mt

@@ -32,6 +32,7 @@ struct LinParams {
   const int32_t* sperm;
   const int32_t* sptr;
   int accumulate;
+  int transpose;  // 1: apply the transposed weight slices (backward w.r.t. x): blocks come with in/out swapped
   void* out;
   int64_t N;
 };
@@ -112,7 +113,9 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
     for (int t = tid; t < kLinK * kLinCols; t += blockDim.x) {
       int uu = t / kLinCols, c = t - uu * kLinCols;
       T v = T(0);
-      if (uu < ku && c < ncols) v = W[(size_t)p.w_off[b] + ((size_t)(u0 + uu) * p.S + s) * mo + c0 + c];
+      if (uu < ku && c < ncols)
+        v = p.transpose ? W[(size_t)p.w_off[b] + ((size_t)(c0 + c) * p.S + s) * mi + (u0 + uu)]
+                        : W[(size_t)p.w_off[b] + ((size_t)(u0 + uu) * p.S + s) * mo + c0 + c];
       ws[uu][c] = v;
     }
     // stage x transposed  xsT[uu][j*d+m] = X[node_j, in_off + (u0+uu)*d + m]
@@ -218,9 +221,10 @@ extern "C" {
 static int linear_fwd_round(int dtype, const mt_lin_block* const* blocks, int num_blocks, int in_dim,
                             int out_dim, int num_species, const void* x, const void* weight,
                             const int32_t* species_perm, const int32_t* species_ptr, int accumulate, void* out,
-                            int64_t N, cudaStream_t st) {
+                            int64_t N, cudaStream_t st, int transpose = 0) {
   LinParams p;
   memset(&p, 0, sizeof(p));
+  p.transpose = transpose;
   p.num_blocks = num_blocks;
   int64_t total = 0;
   for (int b = 0; b < num_blocks; ++b) {
@@ -247,17 +251,8 @@ static int linear_fwd_round(int dtype, const mt_lin_block* const* blocks, int nu
   return MT_OK;
 }
 
-int mt_linear_fwd(int dtype, const mt_lin_block* blocks, int num_blocks, int in_dim, int out_dim,
-                  int num_species, const void* x, const void* weight, const int32_t* species_perm,
-                  const int32_t* species_ptr, int accumulate, void* out, int64_t N, mt_stream stream) {
-  MT_ENTRY_GUARD();
-  MT_REQUIRE(blocks && num_blocks > 0 && num_blocks <= 4 * kLinMaxBlocks, "num_blocks %d not in 1..%d",
-             num_blocks, 4 * kLinMaxBlocks);
-  MT_REQUIRE(in_dim > 0 && out_dim > 0 && num_species >= 1, "bad dims");
-  MT_REQUIRE((species_perm == nullptr) == (species_ptr == nullptr), "species_perm/ptr must be given together");
-  MT_REQUIRE(num_species == 1 || species_ptr != nullptr, "species grouping required when num_species > 1");
-  if (N == 0) return MT_OK;
-  MT_REQUIRE(x && out, "null pointer");
+static int linear_check_blocks(const mt_lin_block* blocks, int num_blocks, int in_dim, int out_dim,
+                               const void* weight) {
   for (int b = 0; b < num_blocks; ++b) {
     const mt_lin_block& k = blocks[b];
     MT_REQUIRE(k.dim >= 1 && k.dim <= kLinRows && k.mul_out > 0 && k.mul_in >= 0, "bad linear block %d", b);
@@ -265,9 +260,16 @@ int mt_linear_fwd(int dtype, const mt_lin_block* blocks, int num_blocks, int in_
     MT_REQUIRE(k.mul_in == 0 || (k.in_off >= 0 && k.in_off + k.mul_in * k.dim <= in_dim), "block %d exceeds in_dim", b);
     MT_REQUIRE(k.mul_in == 0 || weight != nullptr, "null weight");
   }
-  // Blocks that write the same output range (several input irreps of one type feeding one output,
-  // e3nn sums them) must not race: round r holds the r-th block of every distinct output range;
-  // rounds after the first accumulate.  Simplified irreps (every matten model) need one round.
+  return MT_OK;
+}
+
+// Blocks that write the same output range (several input irreps of one type feeding one output,
+// e3nn sums them) must not race: round r holds the r-th block of every distinct output range;
+// rounds after the first accumulate.  Simplified irreps (every matten model) need one round.
+static int linear_rounds(int dtype, const mt_lin_block* blocks, int num_blocks, int in_dim, int out_dim,
+                         int num_species, const void* x, const void* weight, const int32_t* species_perm,
+                         const int32_t* species_ptr, int accumulate, void* out, int64_t N, cudaStream_t st,
+                         int transpose) {
   int round_of[4 * kLinMaxBlocks];
   int max_round = 0;
   for (int b = 0; b < num_blocks; ++b) {
@@ -286,10 +288,49 @@ int mt_linear_fwd(int dtype, const mt_lin_block* blocks, int num_blocks, int in_
       sel[n++] = &blocks[b];
     }
     int rc = linear_fwd_round(dtype, sel, n, in_dim, out_dim, num_species, x, weight, species_perm, species_ptr,
-                              (accumulate || r > 0) ? 1 : 0, out, N, as_stream(stream));
+                              (accumulate || r > 0) ? 1 : 0, out, N, st, transpose);
     if (rc != MT_OK) return rc;
   }
   return MT_OK;
+}
+
+// Backward of the linear w.r.t. x: the transposed weight slices applied to grad_out (train_ops.cu).
+int linear_transposed(int dtype, const mt_lin_block* blocks, int num_blocks, int in_dim, int out_dim,
+                      int num_species, const void* grad_out, const void* weight, const int32_t* species_perm,
+                      const int32_t* species_ptr, int accumulate, void* grad_x, int64_t N, cudaStream_t st) {
+  mt_lin_block tb[4 * kLinMaxBlocks];
+  int n = 0;
+  for (int b = 0; b < num_blocks; ++b) {
+    const mt_lin_block& k = blocks[b];
+    if (k.mul_in == 0) continue;  // zero-fill blocks carry no gradient
+    tb[n] = k;
+    tb[n].in_off = k.out_off; tb[n].out_off = k.in_off; tb[n].mul_in = k.mul_out; tb[n].mul_out = k.mul_in;
+    ++n;
+  }
+  if (!accumulate) {
+    const size_t es = dtype == MT_F64 ? 8 : 4;
+    MT_CUDA_OK(cudaMemsetAsync(grad_x, 0, (size_t)N * in_dim * es, st));
+  }
+  if (n == 0) return MT_OK;
+  return linear_rounds(dtype, tb, n, out_dim, in_dim, num_species, grad_out, weight, species_perm, species_ptr, 1,
+                       grad_x, N, st, 1);
+}
+
+int mt_linear_fwd(int dtype, const mt_lin_block* blocks, int num_blocks, int in_dim, int out_dim,
+                  int num_species, const void* x, const void* weight, const int32_t* species_perm,
+                  const int32_t* species_ptr, int accumulate, void* out, int64_t N, mt_stream stream) {
+  MT_ENTRY_GUARD();
+  MT_REQUIRE(blocks && num_blocks > 0 && num_blocks <= 4 * kLinMaxBlocks, "num_blocks %d not in 1..%d",
+             num_blocks, 4 * kLinMaxBlocks);
+  MT_REQUIRE(in_dim > 0 && out_dim > 0 && num_species >= 1, "bad dims");
+  MT_REQUIRE((species_perm == nullptr) == (species_ptr == nullptr), "species_perm/ptr must be given together");
+  MT_REQUIRE(num_species == 1 || species_ptr != nullptr, "species grouping required when num_species > 1");
+  if (N == 0) return MT_OK;
+  MT_REQUIRE(x && out, "null pointer");
+  int rc = linear_check_blocks(blocks, num_blocks, in_dim, out_dim, weight);
+  if (rc != MT_OK) return rc;
+  return linear_rounds(dtype, blocks, num_blocks, in_dim, out_dim, num_species, x, weight, species_perm,
+                       species_ptr, accumulate, out, N, as_stream(stream), 0);
 }
 
 int mt_gate_fwd(int dtype, const void* x, int in_dim, int out_dim, const int32_t* src_idx,

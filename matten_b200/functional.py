@@ -43,9 +43,8 @@ def edge_sh(vec, lmax: int, normalize: bool = True):
 
 def edge_radial(length, mode, num_basis, start, end, cutoff=True, poly_p=6.0, bessel_w=None):
     if _needs_grad(bessel_w):
-        from . import autograd as A
-
-        return A.EdgeRadialFn.apply(length, bessel_w, mode, num_basis, start, end, cutoff, poly_p)
+        raise NotImplementedError("gradients w.r.t. trainable Bessel frequencies (RadialBasisEdgeEncoding) are not "
+                                  "implemented; no matten model factory wires that module")
     bw = bessel_w.detach() if bessel_w is not None else None
     return ops.edge_radial(length.detach(), mode, num_basis, start, end, cutoff, poly_p, bw)
 
@@ -83,11 +82,16 @@ def conv(handle: ops.ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Ten
 
 def gate(x, tables, affine_a=None, affine_b=None):
     """tables = (in_dim, out_dim, src_idx, gate_idx, act_id, act_cst)"""
-    if _needs_grad(x, affine_a, affine_b):
+    if _needs_grad(affine_a, affine_b):
+        from . import autograd as A
+
+        # trainable affine (BatchNorm parameters in eval mode under autograd): unfused gate, then affine
+        return A.AffineFn.apply(A.GateFn.apply(x, None, None, tables), affine_a, affine_b)
+    if _needs_grad(x):
         from . import autograd as A
 
         return A.GateFn.apply(x, affine_a, affine_b, tables)
-    in_dim, out_dim, src, gidx, act, cst = tables
+    in_dim, out_dim, src, gidx, act, cst = tables[:6]
     return ops.gate_fwd(x.detach(), in_dim, out_dim, src, gidx, act, cst,
                         None if affine_a is None else affine_a.detach(),
                         None if affine_b is None else affine_b.detach())

@@ -167,6 +167,8 @@ class _GateModule(_Buffers):
         self._reg("gate_idx", plan.gate_idx)
         self._reg("act_id", plan.act_id)
         self._reg("act_cst64", plan.act_cst)
+        self._reg("inv_first", plan.inv_first)
+        self._reg("inv_count", plan.inv_count)
         self._cst = {}
 
     def tables(self, dtype):
@@ -174,7 +176,8 @@ class _GateModule(_Buffers):
         if cst is None:
             cst = self.act_cst64.to(dtype)
             self._cst = {(dtype, self.act_cst64.device): cst}
-        return (self.plan.in_dim, self.plan.out_dim, self.src_idx, self.gate_idx, self.act_id, cst)
+        return (self.plan.in_dim, self.plan.out_dim, self.src_idx, self.gate_idx, self.act_id, cst, self.inv_first,
+                self.inv_count)
 
     def forward(self, x, affine_a=None, affine_b=None):
         return F.gate(x, self.tables(x.dtype), affine_a, affine_b)
@@ -229,10 +232,21 @@ class BatchNorm(_Buffers):
         self._reg("feat_idx", feat)
         self._reg("scal_idx", scal.clamp(min=0))
         self._reg("scal_mask", (scal >= 0))
+        self._reg("scal_cols", torch.nonzero(scal >= 0).reshape(-1))
         self.register_buffer("running_mean", torch.zeros(ns))
         self.register_buffer("running_var", torch.ones(nf))
         self.weight = torch.nn.Parameter(torch.ones(nf))
         self.bias = torch.nn.Parameter(torch.zeros(ns))
+
+    def channel_matrix(self, dtype):
+        """[D, num_features] 0/1 matrix summing the 2l+1 columns of every channel (deterministic, unlike index_add)."""
+        key = (dtype, self.feat_idx.device)
+        if getattr(self, "_chan_key", None) != key:
+            D = self.feat_idx.shape[0]
+            m = torch.zeros((D, self.num_features), dtype=dtype, device=self.feat_idx.device)
+            m[torch.arange(D, device=m.device), self.feat_idx] = 1
+            self._chan, self._chan_key = m, key
+        return self._chan
 
     def eval_affine(self, dtype):
         """Per-element (a, b) with ``y = a*x + b`` for eval mode: tiny [D] vectors derived from
@@ -268,6 +282,10 @@ class BatchNorm(_Buffers):
 
 
 def A_affine(x, a, b):
+    if torch.is_grad_enabled() and (x.requires_grad or a.requires_grad or b.requires_grad):
+        from .. import autograd as A
+
+        return A.AffineFn.apply(x, a, b)
     D = x.shape[-1]
     key = (D, x.device)
     t = _IDENT.get(key)
@@ -278,7 +296,7 @@ def A_affine(x, a, b):
         t = (src, gate, act)
         _IDENT[key] = t
     cst = torch.ones(D, dtype=x.dtype, device=x.device)
-    return F.gate(x, (D, D, t[0], t[1], t[2], cst), a, b)
+    return F.gate(x, (D, D, t[0], t[1], t[2], cst, None, None), a, b)
 
 
 _IDENT = {}

@@ -210,6 +210,10 @@ class ConvPlanHandle:
             s.tc_row_wcol, s.tc_sub_hdr, s.tc_sub_slot, s.tc_q_list = [t.data_ptr() for t in self.tc_tables]
             for q in range(4):
                 s.tc_q_count[q] = uvu_plan.tc_q_count[q]
+        self.bw_tables = [t.to(device).contiguous() for t in (uvu_plan.bw_item_hdr, uvu_plan.bw_lane_tab,
+                                                               uvu_plan.bw_path_tab)]
+        s.bw_num_items, s.bw_num_paths = uvu_plan.bw_num_items, uvu_plan.bw_num_paths
+        s.bw_item_hdr, s.bw_lane_tab, s.bw_path_tab = [t.data_ptr() for t in self.bw_tables]
         self.struct = s
         self.mlp_sizes = list(mlp_sizes)
         self.device = torch.device(device)
@@ -249,6 +253,32 @@ def conv_fwd(handle: ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Ten
     return out
 
 
+def conv_bwd(handle: ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Tensor], rowptr, perm, src_sorted,
+             sender_ptr, sender_perm, avg_num_neighbors: Optional[float], num_neigh, grad_out,
+             need_x: bool = True, need_w: bool = True):
+    """Returns (grad_x | None, [grad of every MLP weight] | None)."""
+    lib = _lib.load()
+    x = _req(x, "node_features")
+    sh = _req(sh, "edge_attrs", x.dtype)
+    emb = _req(emb, "edge_embedding", x.dtype)
+    grad_out = _req(grad_out, "grad_out", x.dtype)
+    N, E = x.shape[0], sh.shape[0]
+    ws = [_req(w, f"weight_nn.layer{i}.weight", x.dtype) for i, w in enumerate(mlp_weights)]
+    wptrs = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+    gx = torch.empty_like(x) if need_x else None
+    gws = [torch.empty_like(w) for w in ws] if need_w else None
+    gwptrs = (C.c_void_p * len(ws))(*[g.data_ptr() for g in gws]) if need_w else None
+    if num_neigh is not None:
+        num_neigh = _req(num_neigh, "num_neigh", x.dtype)
+    nbytes = lib.mt_conv_bwd_workspace_bytes(C.byref(handle.struct), _dt(x), N, E)
+    wsb = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
+    check(lib.mt_conv_bwd(C.byref(handle.struct), _dt(x), _p(x), _p(sh), _p(emb), wptrs, _p(rowptr), _p(perm),
+                          _p(src_sorted), _p(sender_ptr), _p(sender_perm),
+                          float(avg_num_neighbors) if avg_num_neighbors is not None else 0.0, _p(num_neigh),
+                          _p(grad_out), _p(gx), gwptrs, _p(wsb), nbytes, N, E, _stream(x)))
+    return gx, gws
+
+
 # ----------------------------------------------------------------- linear --
 class LinPlanHandle:
     def __init__(self, blocks, in_dim: int, out_dim: int, num_species: int, weight_numel: int):
@@ -285,7 +315,65 @@ def linear_fwd(h: LinPlanHandle, x, weight, species_perm=None, species_ptr=None,
     return out.reshape(lead + (h.out_dim,))
 
 
+def linear_bwd(h: LinPlanHandle, x, weight, grad_out, species_perm=None, species_ptr=None, need_x=True,
+               need_w=True):
+    """Returns (grad_x | None, grad_weight (flat) | None)."""
+    lib = _lib.load()
+    x = _req(x, "x")
+    x2 = x.reshape(-1, x.shape[-1])
+    g2 = _req(grad_out, "grad_out", x.dtype).reshape(-1, h.out_dim)
+    weight = _req(weight, "weight", x.dtype)
+    N = x2.shape[0]
+    gx = torch.empty_like(x2) if need_x else None
+    gw = torch.empty(h.weight_numel, dtype=x.dtype, device=x.device) if need_w else None
+    nbytes = lib.mt_linear_bwd_workspace_bytes(_dt(x), h.weight_numel) if need_w else 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
+    check(lib.mt_linear_bwd(_dt(x), h.arr, h.n, h.in_dim, h.out_dim, h.S, h.weight_numel, _p(x2), _p(weight), _p(g2),
+                            _p(species_perm), _p(species_ptr), _p(gx), 0, _p(gw), 0, _p(ws), nbytes, N, _stream(x)))
+    return (gx.reshape(x.shape) if need_x else None), gw
+
+
 # ------------------------------------------------------------------- gate --
+def gate_bwd(x, grad_out, in_dim, out_dim, src_idx, gate_idx, act_id, act_cst, inv_first, inv_count, affine_a=None):
+    lib = _lib.load()
+    x = _req(x, "x")
+    grad_out = _req(grad_out, "grad_out", x.dtype)
+    N = x.numel() // in_dim
+    gx = torch.empty_like(x)
+    check(lib.mt_gate_bwd(_dt(x), _p(x), _p(grad_out), in_dim, out_dim, _p(src_idx), _p(gate_idx), _p(act_id),
+                          _p(act_cst), _p(affine_a), _p(inv_first), _p(inv_count), _p(gx), N, _stream(x)))
+    return gx
+
+
+def col_reduce(a, shift_a=None, b=None, shift_b=None):
+    """out[j] = sum_n (a[n,j] - shift_a[j]) * (b[n,j] - shift_b[j])  (b None: plain column sum)."""
+    lib = _lib.load()
+    a = _req(a, "a")
+    a2 = a.reshape(-1, a.shape[-1])
+    N, dim = a2.shape
+    if b is not None:
+        b = _req(b, "b", a.dtype).reshape(-1, dim)
+    out = torch.empty(dim, dtype=a.dtype, device=a.device)
+    nbytes = lib.mt_col_reduce_workspace_bytes(_dt(a), dim)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+    check(lib.mt_col_reduce(_dt(a), _p(a2), _p(shift_a), _p(b), _p(shift_b), N, dim, _p(out), _p(ws), nbytes,
+                            _stream(a)))
+    return out
+
+
+def affine2(a, ca, b=None, cb=None, cc=None):
+    """ca[j]*a[n,j] + cb[j]*b[n,j] + cc[j]"""
+    lib = _lib.load()
+    a = _req(a, "a")
+    dim = a.shape[-1]
+    N = a.numel() // dim
+    if b is not None:
+        b = _req(b, "b", a.dtype)
+    out = torch.empty_like(a)
+    check(lib.mt_affine2(_dt(a), _p(a), _p(ca), _p(b), _p(cb), _p(cc), _p(out), N, dim, _stream(a)))
+    return out
+
+
 def gate_fwd(x, in_dim: int, out_dim: int, src_idx, gate_idx, act_id, act_cst, affine_a=None, affine_b=None):
     lib = _lib.load()
     x = _req(x, "x")
@@ -313,3 +401,54 @@ def segment_reduce(x, ptr, reduce: str = "sum"):
     check(lib.mt_segment_reduce(_dt(x), _p(x), _p(ptr), dim, B, _MODES[reduce], _p(out), _stream(x)))
     _bump()
     return out
+
+
+def segment_reduce_bwd(grad_out, ptr, N: int, reduce: str):
+    lib = _lib.load()
+    grad_out = _req(grad_out, "grad_out")
+    B, dim = grad_out.shape
+    if _MODES[reduce] > 1:
+        raise NotImplementedError("backward of min/max pooling is not implemented")
+    gx = torch.empty((N, dim), dtype=grad_out.dtype, device=grad_out.device)
+    check(lib.mt_segment_reduce_bwd(_dt(grad_out), _p(grad_out), _p(ptr), dim, B, N, _MODES[reduce], _p(gx),
+                                    _stream(grad_out)))
+    return gx
+
+
+def segment_sum_gather(x, perm, ptr, num_rows: Optional[int] = None):
+    """out[s] = sum of the rows x[perm[i]] for i in [ptr[s], ptr[s+1]) in that order."""
+    lib = _lib.load()
+    x = _req(x, "x")
+    S = ptr.shape[0] - 1
+    dim = x.shape[1]
+    if num_rows is None:
+        num_rows = perm.shape[0] if perm is not None else x.shape[0]
+    out = torch.empty((S, dim), dtype=x.dtype, device=x.device)
+    check(lib.mt_segment_sum_gather(_dt(x), _p(x), _p(perm), _p(ptr), dim, S, num_rows, _p(out), _stream(x)))
+    return out
+
+
+# ------------------------------------------------------- loss / optimiser --
+def mse_loss(pred, target, grad_scale: float = 1.0, want_grad: bool = True):
+    """(loss [1], d loss / d pred * grad_scale | None) -- torch.nn.functional.mse_loss(reduction='mean')."""
+    lib = _lib.load()
+    pred = _req(pred, "pred")
+    target = _req(target, "target", pred.dtype)
+    if pred.shape != target.shape:
+        raise ValueError(f"mse_loss: shapes {tuple(pred.shape)} and {tuple(target.shape)} differ")
+    loss = torch.empty(1, dtype=pred.dtype, device=pred.device)
+    grad = torch.empty_like(pred) if want_grad else None
+    check(lib.mt_mse_loss(_dt(pred), _p(pred), _p(target), pred.numel(), float(grad_scale), _p(loss), _p(grad),
+                          _stream(pred)))
+    return loss, grad
+
+
+def adam_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+              grad_scale: float = 1.0):
+    """In-place torch.optim.Adam update of the flat buffers p, m, v from the flat gradient g."""
+    lib = _lib.load()
+    for name, t in (("p", p), ("g", g), ("m", m), ("v", v)):
+        if not t.is_cuda or not t.is_contiguous() or t.dtype != p.dtype or t.numel() != p.numel():
+            raise ValueError(f"adam_step: `{name}` must be a contiguous CUDA tensor matching the parameters")
+    check(lib.mt_adam_step(_dt(p), _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),
+                           float(eps), float(weight_decay), float(grad_scale), int(step), _stream(p)))

@@ -75,6 +75,7 @@ class UVUPlan:
         self.x_dim, self.y_dim, self.out_dim = in1.dim, in2.dim, self.irreps_mid.dim
         self._build_items()
         self._build_tc()
+        self._build_bwd()
 
     @property
     def irreps_out(self) -> Irreps:
@@ -184,6 +185,46 @@ class UVUPlan:
         self.tc_q_list = ql
         self.tc_q_count = [len(qlist[q]) for q in range(4)]
         self.tc_q_cost = qcost
+
+    def _build_bwd(self):
+        """Tables of the backward kernel (csrc/conv_bwd.cuh).  The backward is organised by INPUT channel:
+        a lane owns one channel (i, u) of ``x`` and walks every path that reads it, so the gradient of the
+        gathered row is a register sum in a fixed path order (no atomics).
+          bw_item_hdr [n,4]   : {l1, cpw, first path, path count}
+          bw_lane_tab [n,32,2]: per lane {u (-1: idle), offset of x[u,:] in the x row}
+          bw_path_tab [m,4]   : {cg_type_id, weight column of u = 0, sh offset, out offset of u = 0}"""
+        by_in: Dict[int, List[UVUPath]] = {}
+        for p in self.paths:
+            by_in.setdefault(p.i_in1, []).append(p)
+        items, path_tab = [], []
+        s1 = self.irreps_in1.slices()
+        for i, (mul, ir1) in enumerate(self.irreps_in1):
+            ps = by_in.get(i, [])  # an input irrep without any path still gets its (zero) gradient written
+            l1 = ir1.l
+            if mul == 0 or l1 > LMAX:
+                continue
+            first = len(path_tab)
+            for p in ps:
+                path_tab.append([cg_type_id(p.l1, p.l2, p.l3), p.w_off, p.y_off, p.out_off])
+            cost = sum(2 * cg_nnz(p.l1, p.l2, p.l3) + 2 * p.l3 + 2 for p in ps)
+            for u0 in range(0, mul, 32):
+                n = min(32, mul - u0)
+                cpw = 1
+                while cpw < n:
+                    cpw *= 2
+                lanes = []
+                for lane in range(32):
+                    c = lane % cpw
+                    lanes.append([u0 + c, s1[i].start + (u0 + c) * (2 * l1 + 1)] if c < n else [-1, 0])
+                items.append((cost, [l1, cpw, first, len(ps)], lanes))
+        if not path_tab:
+            path_tab.append([0, 0, 0, 0])
+        items.sort(key=lambda t: -t[0])
+        self.bw_num_items = len(items)
+        self.bw_num_paths = len(path_tab)
+        self.bw_item_hdr = torch.tensor([t[1] for t in items], dtype=torch.int32)
+        self.bw_lane_tab = torch.tensor([t[2] for t in items], dtype=torch.int32).reshape(len(items), 32, 2)
+        self.bw_path_tab = torch.tensor(path_tab, dtype=torch.int32).reshape(len(path_tab), 4)
 
     # per-edge algorithmic cost, for roofline reporting (SURVEY.md section 8d)
     def cg_macs_per_edge(self) -> int:
@@ -320,6 +361,16 @@ class GatePlan:
         self.gate_idx = torch.tensor(gate, dtype=torch.int32)
         self.act_id = torch.tensor(act, dtype=torch.int32)
         self.act_cst = torch.tensor(cst, dtype=torch.float64)
+        # inverse tables for the backward: input i feeds outputs inv_first[i] .. + inv_count[i] - 1
+        inv_first, inv_count = [0] * self.in_dim, [0] * self.in_dim
+        for j, (si, gi) in enumerate(zip(src, gate)):
+            for i in ((si,) if gi < 0 else (si, gi)):
+                if inv_count[i] == 0:
+                    inv_first[i] = j
+                assert j == inv_first[i] + inv_count[i], "outputs of one input must be contiguous"
+                inv_count[i] += 1
+        self.inv_first = torch.tensor(inv_first, dtype=torch.int32)
+        self.inv_count = torch.tensor(inv_count, dtype=torch.int32)
 
 
 def batchnorm_channel_map(irreps) -> Tuple[torch.Tensor, torch.Tensor, int, int]:
