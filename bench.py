@@ -255,6 +255,39 @@ def run_ours(args):
         ms_e2e = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
         clocks = sampler.stop() if rank == 0 else None
 
+    # ---------------- training step: fwd + bwd + (all-reduce) + Adam (BASELINE config 3 flavour) ----------------
+    train = None
+    if not args.no_train:
+        from matten_b200.train import Trainer
+
+        tmodel = ScalarTensorModel(HP, {"allowed_species": SPECIES}).to(dev)
+        tmodel.load_state_dict(model.state_dict())
+        trainer = Trainer(tmodel, lr=0.01, weight_decay=1e-5)
+        target = torch.randn(B, 6, generator=torch.Generator().manual_seed(1 + rank)).to(dev)
+        tsteps = max(3, args.steps // 4)
+        for _ in range(3):
+            trainer.step(dict(resident), target)
+        barrier()
+        l0 = ops.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(tsteps):
+            loss = trainer.step(dict(resident), target)
+        ev1.record()
+        barrier()
+        ms_train = max_over_ranks(ev0.elapsed_time(ev1) / tsteps)
+        assert torch.isfinite(loss).all()
+        train = {"metric": "crystals/sec (training step: fwd + bwd + Adam, fp32, batch 512 crystals per GPU)",
+                 "value": round(B * world / (ms_train * 1e-3), 1), "unit": "crystals/s",
+                 "ms_per_step": round(ms_train, 4), "steps": tsteps,
+                 "conv_edges_per_sec_fwd_bwd": round(4 * E * world / (ms_train * 1e-3), 1),
+                 "gpu_launches_per_step": round((ops.launch_count() - l0) / tsteps, 1),
+                 "allreduce": (f"NCCL all_reduce of the flat fp32 gradient ({trainer.opt.flat_g.numel()} floats) "
+                               f"over {world} ranks" if world > 1 else "none (1 rank)"),
+                 "loss": round(float(loss), 6)}
+        del trainer, tmodel
+        torch.cuda.empty_cache()
+
     # ---------------- roofline of the dominant kernel (fused conv) ----------------
     peak, peak_src = peaks()
     n_rad = HP["num_radial_basis"]
@@ -298,7 +331,7 @@ def run_ours(args):
                     "ms_per_step": round(ms_e2e, 4), "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches), "launches_per_step": round(launches / args.steps, 1),
-            "roofline": roofline, "clocks": clocks,
+            "roofline": roofline, "clocks": clocks, "train": train,
         }
         if world == 1 and not args.no_cpu_baseline:
             res = cpu_baseline(8, 5, 2)
@@ -316,6 +349,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
