@@ -167,7 +167,7 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
       MT_LAUNCH_OK();
     }
     if (nl > 1) {
-      const size_t smem3 = ((size_t)3 * kHidEB * (kBwdMaxH + 1) + (size_t)kBwdMaxH * kBwdMaxH + p.hid_numel) * sizeof(T);
+      const size_t smem3 = ((size_t)3 * kHidEB * (kBwdMaxH + 1) + (size_t)kBwdMaxH * (kBwdMaxH + 1) + p.hid_numel) * sizeof(T);
       MT_REQUIRE(smem3 <= 227 * 1024, "hidden MLP too large for the backward kernel");
       static thread_local size_t cfg3 = 0;
       if (smem3 > cfg3) {

@@ -59,6 +59,20 @@ struct ConvBwdParams {
   int ncg, grid2, grid3, hid_numel;
 };
 
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, T (&v)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4<double>(const double* p, double (&v)[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
 // last-layer input a_{nl-1}[e][k]: act(z_{nl-2}) * cst, or the embedding itself for a single-layer MLP
 template <typename T>
 __device__ __forceinline__ T last_input(const ConvBwdParams& p, int64_t e, int k) {
@@ -160,7 +174,7 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(const ConvBwdParams p)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int EC = p.chunk_edges;
   int4* spath = reinterpret_cast<int4*>(smem_raw);     // [num_paths]
-  T* hs = reinterpret_cast<T*>(spath + p.num_paths);   // [EC][hs_stride]  (hs_stride is a multiple of 4)
+  T* hs = reinterpret_cast<T*>(spath + p.num_paths);   // [hs_stride >= H][EC] transposed last-layer input
   T* xs = hs + (size_t)EC * p.hs_stride;               // [EC][xs_stride]
   T* ys = xs + (size_t)EC * p.xs_stride;               // [EC][y_dim]
   T* wt = ys + (size_t)EC * p.y_dim;                   // [EC][wt_stride]
@@ -202,32 +216,41 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(const ConvBwdParams p)
         const int el = t / p.y_dim, j = t - el * p.y_dim;
         ys[t] = SH[(size_t)p.perm[c0 + el] * p.y_dim + j];
       }
-      for (int t = tid; t < EC * p.hs_stride; t += blockDim.x) {
-        const int el = t / p.hs_stride, k = t - el * p.hs_stride;
-        hs[t] = (el < ne && k < H) ? last_input<T>(p, (int64_t)c0 + el, k) * inv_sqrt_h : T(0);
+      // a_last / sqrt(H), TRANSPOSED [k][EC] so that the 8 edges of a register pass are one 128-bit broadcast load
+      for (int t = tid; t < EC * H; t += blockDim.x) {
+        const int k = t / EC, el = t - k * EC;  // lanes walk the edges: conflict-free stores
+        hs[(size_t)k * EC + el] = (el < ne) ? last_input<T>(p, (int64_t)c0 + el, k) * inv_sqrt_h : T(0);
       }
       if (tid == 0) s_counter = 0;
       __syncthreads();
       // ------------------------------------------------------------ (A) per-edge weights into shared memory
+      // register tile: 8 edges x 2 columns (c, c + blockDim) per thread
       for (int ep = 0; ep < ne; ep += kBwdET) {
-        for (int c = tid; c < Wn; c += blockDim.x) {
-          T acc[kBwdET];
+        for (int c = tid; c < Wn; c += 2 * blockDim.x) {
+          const int c2 = c + blockDim.x;
+          const bool two = c2 < Wn;
+          T acc0[kBwdET], acc1[kBwdET];
 #pragma unroll
-          for (int i = 0; i < kBwdET; ++i) acc[i] = T(0);
-          for (int k = 0; k < H; k += 4) {
-            T wv[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) wv[q] = (k + q < H) ? Wlast[(size_t)(k + q) * Wn + c] : T(0);
+          for (int i = 0; i < kBwdET; ++i) { acc0[i] = T(0); acc1[i] = T(0); }
+#pragma unroll 4
+          for (int k = 0; k < H; ++k) {
+            const T w0 = Wlast[(size_t)k * Wn + c];
+            const T w1 = two ? Wlast[(size_t)k * Wn + c2] : T(0);
+            T hv[kBwdET];
+            load4<T>(hs + (size_t)k * EC + ep, *reinterpret_cast<T(*)[4]>(&hv[0]));
+            load4<T>(hs + (size_t)k * EC + ep + 4, *reinterpret_cast<T(*)[4]>(&hv[4]));
 #pragma unroll
             for (int i = 0; i < kBwdET; ++i) {
-              const T* hr = hs + (size_t)(ep + i) * p.hs_stride + k;  // rows beyond ne are zero
-#pragma unroll
-              for (int q = 0; q < 4; ++q) acc[i] = fma(hr[q], wv[q], acc[i]);
+              acc0[i] = fma(hv[i], w0, acc0[i]);
+              acc1[i] = fma(hv[i], w1, acc1[i]);
             }
           }
 #pragma unroll
           for (int i = 0; i < kBwdET; ++i)
-            if (ep + i < ne) wt[(size_t)(ep + i) * p.wt_stride + c] = acc[i];
+            if (ep + i < ne) {
+              wt[(size_t)(ep + i) * p.wt_stride + c] = acc0[i];
+              if (two) wt[(size_t)(ep + i) * p.wt_stride + c2] = acc1[i];
+            }
         }
       }
       __syncthreads();
@@ -366,8 +389,8 @@ __global__ void __launch_bounds__(256) mlp_bwd_hidden_kernel(const ConvBwdParams
   T* DA = reinterpret_cast<T*>(smem_raw);   // [kHidEB][RS]  gradient w.r.t. the layer's output activation
   T* DZ = DA + (size_t)kHidEB * RS;         // [kHidEB][RS]
   T* A = DZ + (size_t)kHidEB * RS;          // [kHidEB][RS]  the layer's input activation
-  T* Wl = A + (size_t)kHidEB * RS;          // [<=64*64] current layer, pre-scaled
-  T* accW = Wl + (size_t)kBwdMaxH * kBwdMaxH;  // [hid_numel] running partial sums of this CTA
+  T* Wl = A + (size_t)kHidEB * RS;          // [<=64][fo + 1] current layer, pre-scaled (padded: lanes walk k)
+  T* accW = Wl + (size_t)kBwdMaxH * RS;     // [hid_numel] running partial sums of this CTA
   const int tid = threadIdx.x;
   for (int t = tid; t < p.hid_numel; t += blockDim.x) accW[t] = T(0);
   const int H = p.sizes[p.nl - 1];
@@ -391,7 +414,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_hidden_kernel(const ConvBwdParams
       const T s = T(1) / sqrt(T(fi));
       const T* __restrict__ Wg = static_cast<const T*>(p.w[l]);
       __syncthreads();
-      for (int t = tid; t < fi * fo; t += blockDim.x) Wl[t] = Wg[t] * s;
+      for (int t = tid; t < fi * fo; t += blockDim.x) Wl[(t / fo) * (fo + 1) + (t % fo)] = Wg[t] * s;
       const T* Z = static_cast<const T*>(p.z[l]);
       for (int t = tid; t < kHidEB * fo; t += blockDim.x) {
         const int el = t / fo, j = t - el * fo;
@@ -422,7 +445,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_hidden_kernel(const ConvBwdParams
         for (int t = tid; t < kHidEB * fi; t += blockDim.x) {
           const int el = t / fi, k = t - el * fi;
           T acc = T(0);
-          for (int j = 0; j < fo; ++j) acc = fma(DZ[el * RS + j], Wl[k * fo + j], acc);
+          for (int j = 0; j < fo; ++j) acc = fma(DZ[el * RS + j], Wl[k * (fo + 1) + j], acc);
           DA[el * RS + k] = acc;
         }
       }

@@ -11,6 +11,7 @@ Init-time planners: turn irreps into the flat tables the CUDA kernels consume.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -121,13 +122,20 @@ class UVUPlan:
             for u in range(p.mul):
                 cols.append((p.w_off + u, p.x_off + u * (2 * p.l1 + 1), p.y_off, p.out_off + u * (2 * p.l3 + 1)))
         subs = []  # dict(type, cpw, cols, cost)
+        # A (sub-item, node) unit is one dependent chain on one warp, and a chunk holds only ~2 nodes, so the
+        # slowest unit of a chunk sets its duration.  Heavy types are therefore cut into sub-items of 16 or 8
+        # columns (cpw): such a sub-item runs its columns on 32/cpw edge phases, i.e. 32/cpw times shorter.
+        unit_cost = float(os.environ.get("MT_TC_UNIT_COST", "12.5"))
         for (l1, l2, l3), cols in by_type.items():
             base = cg_nnz(l1, l2, l3) * 1.5 + 2 * l1 + 2 * l2 + 2 * l3 + 9
             for c0 in range(0, len(cols), 32):
                 chunk = cols[c0:c0 + 32]
                 cpw = 32 if len(chunk) > 16 else (16 if len(chunk) > 8 else 8)
-                subs.append({"type": cg_type_id(l1, l2, l3), "cpw": cpw, "cols": chunk, "cost": base * cpw / 32.0,
-                             "d3": 2 * l3 + 1})
+                while cpw > 8 and base * cpw / 32.0 > unit_cost:
+                    cpw //= 2
+                for s0 in range(0, len(chunk), cpw):
+                    subs.append({"type": cg_type_id(l1, l2, l3), "cpw": cpw, "cols": chunk[s0:s0 + cpw],
+                                 "cost": base * cpw / 32.0, "d3": 2 * l3 + 1})
         # pack: cpw == 32 sub-items own a group; smaller ones share groups (first fit, large first)
         groups = []  # list of list of (sub index, lane0)
         for i, sb in enumerate(subs):
