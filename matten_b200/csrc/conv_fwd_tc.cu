@@ -7,6 +7,16 @@ namespace mt {
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// widest chunk (MMA N) whose staging buffers fit the shared memory; 0: none
+static int tc_pick_ne(const mt_conv_plan* plan) {
+  const int y_pad = (plan->y_dim + 3) & ~3;
+  for (int ne = tc_chunk_cols(plan->tc_num_tiles); ne >= 64; ne >>= 1) {
+    const TcSmemLayout L = tc_smem_layout(plan->tc_num_tiles, plan->x_dim, y_pad, plan->tc_num_sub, ne);
+    if (L.total + 512 <= (size_t)227 * 1024) return ne;  // dynamic + static shared memory must fit 227 KB
+  }
+  return 0;
+}
+
 static bool tc_plan_qualifies(const mt_conv_plan* plan) {
   if (plan->tc_num_tiles <= 0 || plan->tc_num_tiles > kTcMaxTiles) return false;
   if (plan->tc_num_sub <= 0 || plan->tc_num_sub > kTcMaxSub) return false;
@@ -15,9 +25,7 @@ static bool tc_plan_qualifies(const mt_conv_plan* plan) {
   for (int i = 0; i < plan->mlp_num_layers; ++i)
     if (plan->mlp_sizes[i] > kTcK) return false;
   if (plan->x_dim > 65535 || plan->y_dim > 252 || (plan->x_dim & 3) != 0) return false;  // 16-byte bulk copies
-  const int y_pad = (plan->y_dim + 3) & ~3;
-  const TcSmemLayout L = tc_smem_layout(plan->tc_num_tiles, plan->x_dim, y_pad, plan->tc_num_sub);
-  return L.total + 512 <= (size_t)227 * 1024;  // dynamic + static shared memory must fit 227 KB
+  return tc_pick_ne(plan) > 0;
 }
 
 size_t conv_fwd_tc_workspace_bytes(const mt_conv_plan* plan, int64_t E) {
@@ -74,7 +82,8 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
   }
   const char* dbg = getenv("MT_CONV_TC_DEBUG");
   p.dbg = (dbg && *dbg) ? reinterpret_cast<long long*>(strtoull(dbg, nullptr, 10)) : nullptr;
-  const TcSmemLayout L = tc_smem_layout(p.num_tiles, p.x_dim, p.y_pad, p.num_sub);
+  const int NE = tc_pick_ne(plan);
+  const TcSmemLayout L = tc_smem_layout(p.num_tiles, p.x_dim, p.y_pad, p.num_sub, NE);
   if (E > 0) {
     int64_t g = ceil_div<int64_t>(E, kPrepThreads);
     const int64_t cap = (int64_t)kNumSMs * 16;
@@ -85,12 +94,20 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
   int64_t grid = kNumSMs;
   if (grid > N) grid = N;
   if (grid < 1) grid = 1;
-  static thread_local size_t configured = 0;
-  if (L.total > configured) {
-    MT_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    configured = L.total;
+  static thread_local size_t configured[3] = {0, 0, 0};
+  const int vi = NE == 256 ? 0 : (NE == 128 ? 1 : 2);
+  if (L.total > configured[vi]) {
+    if (NE == 256)
+      MT_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    else if (NE == 128)
+      MT_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    else
+      MT_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    configured[vi] = L.total;
   }
-  conv_fwd_tc_kernel<<<(unsigned)grid, kTcThreads, L.total, st>>>(p);
+  if (NE == 256) conv_fwd_tc_kernel<256><<<(unsigned)grid, kTcThreads, L.total, st>>>(p);
+  else if (NE == 128) conv_fwd_tc_kernel<128><<<(unsigned)grid, kTcThreads, L.total, st>>>(p);
+  else conv_fwd_tc_kernel<64><<<(unsigned)grid, kTcThreads, L.total, st>>>(p);
   MT_LAUNCH_OK();
   *used = 1;
   return MT_OK;

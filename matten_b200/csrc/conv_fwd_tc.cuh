@@ -33,9 +33,11 @@
 
 namespace mt {
 
-constexpr int kTcNE = 64;             // columns (padded edges) per chunk == MMA N
+// columns (padded edges) per chunk == MMA N: 2 stages x MT tiles x NE columns must fit the 512 TMEM columns, so
+// small plans take wider chunks (more nodes per chunk: more units to balance, fewer producer round trips)
+__host__ __device__ constexpr int tc_chunk_cols(int MT) { return MT <= 1 ? 256 : (MT == 2 ? 128 : 64); }
 constexpr int kTcK = 32;              // padded size of the last hidden layer == MMA K total
-constexpr int kTcProducerWarps = 4;   // warp 0: chunks + copies, warp 1: MMA issue, warps 2-3 idle
+constexpr int kTcProducerWarps = 4;   // warp 0: chunks + plane / sh copies, warp 1: MMA issue, warps 2-3: x-row copies
 constexpr int kTcConsumerWarps = 28;  // 7 per TMEM quarter: every warp is a latency-bound dependent chain, so
                                       // throughput comes from the warp count (1024 threads, 64 registers each)
 constexpr int kTcThreads = 32 * (kTcProducerWarps + kTcConsumerWarps);
@@ -46,6 +48,8 @@ constexpr int kTcD = 5;               // 2*lmax+1 of the types this kernel handl
 
 // debugging aid: per-warp progress codes of CTA `dbg_block` into a host-visible buffer (MT_CONV_TC_DEBUG)
 #define MT_DBG(code) do { if (p.dbg && (threadIdx.x & 31) == 0) ((volatile long long*)p.dbg)[256 + blockIdx.x * 32 + (threadIdx.x >> 5)] = (long long)(code); } while (0)
+// phase timing of CTA 0 (MT_CONV_TC_DEBUG = device pointer to >= 16384 int64): slot layout in tools/tc_debug.py
+#define MT_TACC(var) do { if (p.dbg && blockIdx.x == 0) { const long long _n = clock64(); (var) += _n - _tl; _tl = _n; } } while (0)
 #define MT_DBG_BLOCK(code) do { if (p.dbg && threadIdx.x == 0) ((volatile long long*)p.dbg)[blockIdx.x] = (long long)(code); } while (0)
 
 struct ConvTcParams {
@@ -200,6 +204,8 @@ struct __align__(16) TcMeta {
   short cb[kTcMaxNodes];             // first column of the node (multiple of 4)
   short ngrp[kTcMaxNodes];           // padded edge count / 4
   unsigned char first[kTcMaxNodes];  // 1: this chunk holds the node's first edges (plain store), 0: accumulate
+  int rlo[kTcMaxNodes];              // first receiver-sorted edge of the node's piece in this chunk
+  int deg[kTcMaxNodes];              // its (unpadded) edge count
 };
 
 // packed per-lane slot of a sub-item (8 bytes)
@@ -223,20 +229,20 @@ struct TcSmemLayout {
   size_t total;
 };
 __host__ __device__ inline size_t tc_align16(size_t v) { return (v + 15) & ~(size_t)15; }
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int MT, int x_dim, int y_pad, int num_sub) {
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int MT, int x_dim, int y_pad, int num_sub, int NE) {
   TcSmemLayout L;
   size_t o = 0;
   L.a_off = o;
   L.a_plane = (size_t)MT * 128 * kTcK * 2;
   o += 3 * L.a_plane;
   L.b_off = o;
-  L.b_plane = (size_t)kTcNE * kTcK * 2;
+  L.b_plane = (size_t)NE * kTcK * 2;
   o += 3 * L.b_plane;
   L.x_off = o;
-  L.x_buf = (size_t)kTcNE * x_dim * 4;
+  L.x_buf = (size_t)NE * x_dim * 4;
   o += 2 * L.x_buf;
   L.y_off = o;
-  L.y_buf = (size_t)kTcNE * y_pad * 4;
+  L.y_buf = (size_t)NE * y_pad * 4;
   o += 2 * L.y_buf;
   L.meta_off = o;
   o += 2 * tc_align16(sizeof(TcMeta));
@@ -406,16 +412,17 @@ __device__ __forceinline__ void tc_unit(uint32_t taddr, const float* __restrict_
   }
 }
 
+template <int NE>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];  // no swizzle: descriptors need 16 B alignment
-  __shared__ uint64_t bar_full[2], bar_empty[2], bar_bready, bar_bfree;
+  __shared__ uint64_t bar_full[2], bar_empty[2], bar_go[2], bar_bready, bar_bfree;
   __shared__ uint32_t s_tmem_base;
   __shared__ int s_cnt[2][4];
   __shared__ int s_mma_b;  // buffer of the chunk handed to the MMA warp (-1: terminate)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int MT = p.num_tiles;
-  const TcSmemLayout L = tc_smem_layout(MT, p.x_dim, p.y_pad, p.num_sub);
+  const TcSmemLayout L = tc_smem_layout(MT, p.x_dim, p.y_pad, p.num_sub, NE);
   unsigned char* sA = smem + L.a_off;
   unsigned char* sB = smem + L.b_off;
   TcMeta* meta0 = reinterpret_cast<TcMeta*>(smem + L.meta_off);
@@ -423,8 +430,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
   TcSlot* sSlot = reinterpret_cast<TcSlot*>(smem + L.slot_off);
   uint32_t* sHdr = reinterpret_cast<uint32_t*>(smem + L.hdr_off);
   unsigned char* sQ = smem + L.qlist_off;
-  const uint32_t tmem_cols = (2 * MT * kTcNE <= 32) ? 32 : (2 * MT * kTcNE <= 64) ? 64 : (2 * MT * kTcNE <= 128) ? 128
-                             : (2 * MT * kTcNE <= 256) ? 256 : 512;
+  const uint32_t tmem_cols = (2 * MT * NE <= 32) ? 32 : (2 * MT * NE <= 64) ? 64 : (2 * MT * NE <= 128) ? 128
+                             : (2 * MT * NE <= 256) ? 256 : 512;
 
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
@@ -432,6 +439,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
     mbar_init(&bar_full[1], 2);
     mbar_init(&bar_empty[0], kTcConsumerWarps);
     mbar_init(&bar_empty[1], kTcConsumerWarps);
+    mbar_init(&bar_go[0], 1);
+    mbar_init(&bar_go[1], 1);
     mbar_init(&bar_bready, 1);
     mbar_init(&bar_bfree, 1);
     fence_barrier_init();
@@ -513,18 +522,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
     }
     int e_carry = -1;  // >= 0: the next chunk continues node n_cur at this global edge
     int b_uses = 0;    // chunks that loaded the h planes so far
+    long long _tl = clock64(), t_we = 0, t_meta = 0, t_wb = 0, t_pad = 0, t_issue = 0, n_chunks = 0;
     const uint32_t xrow_bytes = (uint32_t)p.x_dim * 4, yrow_bytes = (uint32_t)p.y_pad * 4;
     for (int k = 0;; ++k) {
       const int b = k & 1;
       TcMeta& M = b ? *meta1 : *meta0;
       MT_DBG(1000 + k * 10 + 0);
-      if (lane == 0) mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);  // consumers released buffer b
-      MT_DBG(1000 + k * 10 + 1);
-      __syncwarp();
       if (n_cur >= n_end) {
+        if (lane == 0) mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);  // consumers released buffer b
+        __syncwarp();
         if (lane == 0) {
           M.nnodes = -1;
           M.ncols = 0;
+          mbar_arrive(&bar_go[b]);  // the x-row warps see the terminator
           if (b_uses > 0) mbar_wait(&bar_bfree, (b_uses - 1) & 1, 20);  // the MMA warp is done with its last chunk
           s_mma_b = -1;
           mbar_arrive(&bar_bready);  // terminator for the MMA warp
@@ -541,8 +551,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
       if (lane == 0 && e_carry >= 0) r_lo = e_carry;
       int deg = r_hi - r_lo;
       bool split = false;
-      if (lane == 0 && deg > kTcNE) {  // node larger than a chunk: take 64 edges now, the rest next time
-        deg = kTcNE;
+      if (lane == 0 && deg > NE) {  // node larger than a chunk: take 64 edges now, the rest next time
+        deg = NE;
         split = true;
       }
       const int degp = (deg + 3) & ~3;
@@ -552,24 +562,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
         const int t = __shfl_up_sync(0xffffffffu, cum, o);
         if (lane >= o) cum += t;
       }
-      const unsigned fm = __ballot_sync(0xffffffffu, in_range && cum <= kTcNE);
+      const unsigned fm = __ballot_sync(0xffffffffu, in_range && cum <= NE);
       int m = (fm == 0xffffffffu) ? 32 : (__ffs(~fm) - 1);  // leading run of nodes that fit
       const bool split0 = __shfl_sync(0xffffffffu, (int)split, 0) != 0;
       if (split0) m = 1;
       const bool mine = lane < m;
       const int cb = cum - degp;
-      if (mine) {
-        M.node_id[lane] = (int)cand;
-        M.cb[lane] = (short)cb;
-        M.ngrp[lane] = (short)(degp >> 2);
-        M.first[lane] = (lane == 0 && e_carry >= 0) ? 0 : 1;
-        M.den[lane] = p.num_neigh ? sqrtf(p.num_neigh[cand]) : sqrtf(p.avg);
-      }
+      const float den = mine ? (p.num_neigh ? sqrtf(p.num_neigh[cand]) : sqrtf(p.avg)) : 0.f;
       const int ncols = __shfl_sync(0xffffffffu, cum, m - 1);
       const int my_edges = mine ? deg : 0;
       int tot_edges = my_edges;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) tot_edges += __shfl_xor_sync(0xffffffffu, tot_edges, o);
+      // unpadded and consecutive in the sorted edge list (always, for whole nodes): the chunk's columns are ONE
+      // contiguous edge range -> one copy per plane segment instead of one per node
+      const bool contiguous = (ncols == tot_edges);
+      const int r_first = __shfl_sync(0xffffffffu, r_lo, 0);
+      MT_TACC(t_meta);
+      // ---- everything above only read global memory; now wait until the consumers released buffer b
+      if (lane == 0) mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);
+      MT_DBG(1000 + k * 10 + 1);
+      __syncwarp();
+      MT_TACC(t_we);
+      if (mine) {
+        M.node_id[lane] = (int)cand;
+        M.cb[lane] = (short)cb;
+        M.ngrp[lane] = (short)(degp >> 2);
+        M.first[lane] = (lane == 0 && e_carry >= 0) ? 0 : 1;
+        M.den[lane] = den;
+        M.rlo[lane] = r_lo;
+        M.deg[lane] = deg;
+      }
       const bool continues = (e_carry >= 0);
       if (lane == 0) {
         M.nnodes = m;
@@ -584,6 +607,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
       if (ncols == 0) {
         if (lane == 0) {
           s_cnt[b][0] = 0; s_cnt[b][1] = 0; s_cnt[b][2] = 0; s_cnt[b][3] = 0;
+          mbar_arrive(&bar_go[b]);
           mbar_arrive(&bar_full[b]);  // nothing to copy, no MMA: both arrivals from here
           mbar_arrive(&bar_full[b]);
         }
@@ -593,14 +617,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
           if (b_uses > 0) mbar_wait(&bar_bfree, (b_uses - 1) & 1, 21);  // previous MMAs have consumed the h planes
         }
         __syncwarp();
+        MT_TACC(t_wb);
         MT_DBG(1000 + k * 10 + 2);
         // pad rows of the h planes must be zero (zero weights for pad columns)
-        for (int j = 0; j < m; ++j) {
+        for (int j = 0; j < (contiguous ? 0 : m); ++j) {
           const int dj = __shfl_sync(0xffffffffu, deg, j), cj = __shfl_sync(0xffffffffu, cb, j);
           const int npad = ((dj + 3) & ~3) - dj;
           for (int t = lane; t < npad * 12; t += 32) {
             const int r = t / 12, pg = t - r * 12;
-            *reinterpret_cast<uint4*>(sB + (size_t)(pg >> 2) * L.b_plane + (size_t)(pg & 3) * kTcNE * 16 +
+            *reinterpret_cast<uint4*>(sB + (size_t)(pg >> 2) * L.b_plane + (size_t)(pg & 3) * NE * 16 +
                                       (size_t)(cj + dj + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
           }
         }
@@ -610,32 +635,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
           s_mma_b = b;
           mbar_arrive_expect_tx(&bar_full[b], (uint32_t)tot_edges * (xrow_bytes + yrow_bytes));
           mbar_arrive_expect_tx(&bar_bready, (uint32_t)tot_edges * 16u * 12u);
+          mbar_arrive(&bar_go[b]);  // warps 2-3 issue the gathered x rows (one bulk copy per edge) from here
         }
         __syncwarp();
+        MT_TACC(t_pad);
         MT_DBG(1000 + k * 10 + 3);
-        // bulk copies: per node 12 plane segments + the sh rows (contiguous: sorted order), per edge one x row
-        for (int j = 0; j < m; ++j) {
+        // bulk copies: 12 plane segments + the sh rows per node (contiguous: sorted order) -- or per chunk when the
+        // chunk's columns are one contiguous edge range; the x rows (one per edge) are issued by warps 2-3
+        if (contiguous) {
+          if (lane < 12) {
+            const int pl = lane >> 2, g = lane & 3;
+            bulk_g2s(sB + (size_t)pl * L.b_plane + (size_t)g * NE * 16,
+                     reinterpret_cast<const unsigned char*>(p.hplanes) + ((size_t)(pl * 4 + g) * p.E + r_first) * 16,
+                     (uint32_t)tot_edges * 16u, &bar_bready);
+          } else if (lane == 12) {
+            bulk_g2s(ys, p.ysorted + (size_t)r_first * p.y_pad, (uint32_t)tot_edges * yrow_bytes, &bar_full[b]);
+          }
+        }
+        for (int j = 0; j < (contiguous ? 0 : m); ++j) {
           const int dj = __shfl_sync(0xffffffffu, deg, j), cj = __shfl_sync(0xffffffffu, cb, j);
           const int rj = __shfl_sync(0xffffffffu, r_lo, j);
           if (dj == 0) continue;
           if (lane < 12) {
             const int pl = lane >> 2, g = lane & 3;
-            bulk_g2s(sB + (size_t)pl * L.b_plane + (size_t)g * kTcNE * 16 + (size_t)cj * 16,
+            bulk_g2s(sB + (size_t)pl * L.b_plane + (size_t)g * NE * 16 + (size_t)cj * 16,
                      reinterpret_cast<const unsigned char*>(p.hplanes) + ((size_t)(pl * 4 + g) * p.E + rj) * 16,
                      (uint32_t)dj * 16u, &bar_bready);
           } else if (lane == 12) {
             bulk_g2s(ys + (size_t)cj * p.y_pad, p.ysorted + (size_t)rj * p.y_pad, (uint32_t)dj * yrow_bytes,
                      &bar_full[b]);
           }
-          for (int e = lane; e < dj; e += 32)
-            bulk_g2s(xs + (size_t)(cj + e) * p.x_dim, p.x + (size_t)p.src[rj + e] * p.x_dim, xrow_bytes, &bar_full[b]);
         }
         ++b_uses;
+        ++n_chunks;
+        MT_TACC(t_issue);
         MT_DBG(1000 + k * 10 + 4);
       }
       // advance
       if (split0) {
-        e_carry = __shfl_sync(0xffffffffu, r_lo, 0) + kTcNE;
+        e_carry = __shfl_sync(0xffffffffu, r_lo, 0) + NE;
         if (e_carry >= __shfl_sync(0xffffffffu, r_hi, 0)) {  // exactly consumed
           e_carry = -1;
           n_cur += 1;
@@ -645,12 +683,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
         n_cur += m;
       }
     }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) {
+      p.dbg[8192 + 0] = t_we; p.dbg[8192 + 1] = t_meta; p.dbg[8192 + 2] = t_wb; p.dbg[8192 + 3] = t_pad;
+      p.dbg[8192 + 4] = t_issue; p.dbg[8192 + 6] = n_chunks;
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ================================================================ gathered x rows: one bulk copy per edge
+    // (a UBLKCP is issued lane by lane, ~100 cycles each: two warps on two schedulers halve the issue time)
+    const int part = warp - 2;
+    const uint32_t xrow_bytes = (uint32_t)p.x_dim * 4;
+    long long _tl = clock64(), t_wg = 0, t_cp = 0;
+    for (int k = 0;; ++k) {
+      const int b = k & 1;
+      const TcMeta& M = b ? *meta1 : *meta0;
+      if (lane == 0) mbar_wait(&bar_go[b], (k >> 1) & 1, 50 + b);
+      __syncwarp();
+      MT_TACC(t_wg);
+      const int nn = M.nnodes;
+      if (nn < 0) break;
+      if (M.ncols > 0) {
+        float* xs = reinterpret_cast<float*>(smem + L.x_off + (size_t)b * L.x_buf);
+        for (int j = 0; j < nn; ++j) {
+          const int dj = M.deg[j], cj = M.cb[j], rj = M.rlo[j];
+          for (int e = 2 * lane + part; e < dj; e += 64)
+            bulk_g2s(xs + (size_t)(cj + e) * p.x_dim, p.x + (size_t)p.src[rj + e] * p.x_dim, xrow_bytes, &bar_full[b]);
+        }
+      }
+      MT_TACC(t_cp);
+    }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 10 + 2 * part] = t_wg; p.dbg[8192 + 11 + 2 * part] = t_cp; }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    const uint32_t idesc = make_idesc_bf16(128, kTcNE);
-    const uint32_t a_lbo = (uint32_t)MT * 128 * 16, b_lbo = (uint32_t)kTcNE * 16;
+    const uint32_t idesc = make_idesc_bf16(128, NE);
+    const uint32_t a_lbo = (uint32_t)MT * 128 * 16, b_lbo = (uint32_t)NE * 16;
     const uint64_t a_desc0 = make_kmajor_desc(smem_u32(sA), a_lbo, 128);
     const uint64_t b_desc0 = make_kmajor_desc(smem_u32(sB), b_lbo, 128);
+    long long _tl = clock64(), t_wr = 0, t_mma = 0;
     for (int k = 0;; ++k) {  // k counts the chunks that carry edges (and the terminator)
       MT_DBG(2000 + k * 10 + 0);
       // lane 0 alone reads the hand-over word: by the time the other lanes get here the producer may already
@@ -662,6 +730,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
       }
       b = __shfl_sync(0xffffffffu, b, 0);
       MT_DBG(2000 + k * 10 + 1);
+      MT_TACC(t_wr);
       if (b < 0) break;
       if (lane == 0) {
         tc_fence_after();
@@ -669,7 +738,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
         const int pa[6] = {0, 2, 1, 0, 1, 0};
         const int pb[6] = {2, 0, 1, 1, 0, 0};
         for (int t = 0; t < MT; ++t) {
-          const uint32_t d = tmem_base + (uint32_t)((b * MT + t) * kTcNE);
+          const uint32_t d = tmem_base + (uint32_t)((b * MT + t) * NE);
           uint32_t accum = 0;
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
@@ -687,17 +756,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
         umma_commit(&bar_bfree);
       }
       __syncwarp();
+      MT_TACC(t_mma);
       MT_DBG(2000 + k * 10 + 2);
     }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 8] = t_wr; p.dbg[8192 + 9] = t_mma; }
   } else if (warp >= kTcProducerWarps) {
     // ================================================================ consumers
     const int q = warp & 3;
     const int nsubq = p.q_count[q];
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+    long long _tl = clock64(), t_wf = 0, t_work = 0;
     for (int k = 0;; ++k) {
       const int b = k & 1;
       MT_DBG(3000 + k * 100 + 0);
       mbar_wait(&bar_full[b], (k >> 1) & 1, 40 + b);
+      MT_TACC(t_wf);
       MT_DBG(3000 + k * 100 + 1);
       tc_fence_after();
       const TcMeta& M = b ? *meta1 : *meta0;
@@ -719,12 +792,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
         const int d3 = hd >> 28;
         const TcSlot slot = sSlot[sub * 32 + lane];
         const int cb = M.cb[nj], ngrp = M.ngrp[nj];
+        const long long u0 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;
         float acc[kTcD];
 #pragma unroll
         for (int m = 0; m < kTcD; ++m) acc[m] = 0.f;
         __syncwarp();
         if (ngrp > 0) {
-          const uint32_t taddr = tmem_base + lane_base + (uint32_t)((b * MT + tile) * kTcNE + cb);
+          const uint32_t taddr = tmem_base + lane_base + (uint32_t)((b * MT + tile) * NE + cb);
           const float* xp = xs + (size_t)cb * p.x_dim + slot.xoff;
           const float* yp = ys + (size_t)cb * p.y_pad + slot.yoff;
           const int src_lane = (lane0 + (lane & (cpw - 1))) & 31;
@@ -741,6 +815,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
         for (int off = cpw; off < 32; off <<= 1) {
 #pragma unroll
           for (int m = 0; m < kTcD; ++m) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], off);
+        }
+        if (p.dbg && blockIdx.x == 0 && lane == 0) {
+          atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg) + 8192 + 128 + sub, (unsigned long long)(clock64() - u0));
+          atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg) + 8192 + 256 + sub, 1ull);
         }
         if (slot.valid && lane < cpw) {
           float* o = p.out + (size_t)M.node_id[nj] * p.out_dim + slot.ooff;
@@ -761,7 +839,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_empty[b]);
+      MT_TACC(t_work);
     }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 16 + 2 * warp] = t_wf; p.dbg[8192 + 17 + 2 * warp] = t_work; }
   }
   // ---------------------------------------------------------------- teardown
   MT_DBG(9000);

@@ -125,33 +125,45 @@ class UVUPlan:
         # A (sub-item, node) unit is one dependent chain on one warp, and a chunk holds only ~2 nodes, so the
         # slowest unit of a chunk sets its duration.  Heavy types are therefore cut into sub-items of 16 or 8
         # columns (cpw): such a sub-item runs its columns on 32/cpw edge phases, i.e. 32/cpw times shorter.
-        unit_cost = float(os.environ.get("MT_TC_UNIT_COST", "12.5"))
+        # Cost model: measured cycles per (sub-item, node) unit of the bench graph (tools/tc_debug.py, r1): a
+        # lane == row unit costs 3.5 + 0.28 nnz + 0.35 (D1 + D2 - 2) kcycles; a packed (cpw 8 / 16) unit is NOT
+        # cheaper than a full one (5.3 + 0.145 nnz): its columns x edge phases keep all 32 lanes busy for as many
+        # iterations.  Splitting full types into packed ones (MT_TC_UNIT_COST < 100) therefore does not pay.
+        unit_cost = float(os.environ.get("MT_TC_UNIT_COST", "100"))
         for (l1, l2, l3), cols in by_type.items():
-            base = cg_nnz(l1, l2, l3) * 1.5 + 2 * l1 + 2 * l2 + 2 * l3 + 9
+            nnz = cg_nnz(l1, l2, l3)
+            full = 3.5 + 0.28 * nnz + 0.35 * (2 * l1 + 2 * l2)
+            packed = 5.3 + 0.145 * nnz
             for c0 in range(0, len(cols), 32):
                 chunk = cols[c0:c0 + 32]
                 cpw = 32 if len(chunk) > 16 else (16 if len(chunk) > 8 else 8)
-                while cpw > 8 and base * cpw / 32.0 > unit_cost:
+                while cpw > 8 and full * cpw / 32.0 > unit_cost:
                     cpw //= 2
                 for s0 in range(0, len(chunk), cpw):
                     subs.append({"type": cg_type_id(l1, l2, l3), "cpw": cpw, "cols": chunk[s0:s0 + cpw],
-                                 "cost": base * cpw / 32.0, "d3": 2 * l3 + 1})
-        # pack: cpw == 32 sub-items own a group; smaller ones share groups (first fit, large first)
-        groups = []  # list of list of (sub index, lane0)
+                                 "cost": full if cpw == 32 else packed, "d3": 2 * l3 + 1})
+        # pack: cpw == 32 sub-items own a group of 32 TMEM lanes; smaller ones share groups.  A packed sub-item
+        # costs as much as a full one, so the packed ones are spread over as many groups as the tile count
+        # leaves free (longest-processing-time first), not squeezed into the fewest.
+        groups = []  # dict(subs=[(sub index, lane0)], used=lanes)
         for i, sb in enumerate(subs):
             if sb["cpw"] == 32:
                 groups.append({"subs": [(i, 0)], "used": 32})
-        small = sorted([i for i, sb in enumerate(subs) if sb["cpw"] < 32], key=lambda i: -subs[i]["cpw"])
-        packed = []
+        small = sorted([i for i, sb in enumerate(subs) if sb["cpw"] < 32], key=lambda i: -subs[i]["cost"])
+        n_full = len(groups)
+        lanes_small = sum(subs[i]["cpw"] for i in small)
+        MT = (n_full + (lanes_small + 31) // 32 + 3) // 4
+        packed = [{"subs": [], "used": 0, "cost": 0.0} for _ in range(max(4 * MT - n_full, 0))] if small else []
         for i in small:
-            for g in packed:
-                if g["used"] + subs[i]["cpw"] <= 32:
-                    g["subs"].append((i, g["used"]))
-                    g["used"] += subs[i]["cpw"]
-                    break
-            else:
-                packed.append({"subs": [(i, 0)], "used": subs[i]["cpw"]})
-        groups += packed
+            fits = [g for g in packed if g["used"] + subs[i]["cpw"] <= 32]
+            if not fits:  # fragmentation: one more group (MT is recomputed below)
+                packed.append({"subs": [], "used": 0, "cost": 0.0})
+                fits = [packed[-1]]
+            g = min(fits, key=lambda g: g["cost"])
+            g["subs"].append((i, g["used"]))
+            g["used"] += subs[i]["cpw"]
+            g["cost"] += subs[i]["cost"]
+        groups += [g for g in packed if g["subs"]]
         MT = (len(groups) + 3) // 4
         self.tc_num_tiles = 0
         if MT > 4 or len(subs) > 64:
