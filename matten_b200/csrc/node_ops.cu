@@ -14,9 +14,26 @@ namespace mt {
 //   weight slice staged in shared memory (register-tiled 4x4 FMA micro-kernel).
 // =========================================================================
 constexpr int kLinMaxBlocks = 24;
-constexpr int kLinRows = 64;  // (node, m) rows per CTA
-constexpr int kLinCols = 64;  // output channels per CTA
-constexpr int kLinK = 32;     // u-chunk
+constexpr int kLinOut = 4096;    // outputs per CTA tile: rows x cols, 256 threads x (4 x 4)
+constexpr int kLinStage = 8192;  // staged x elements per k-chunk (rows x KC)
+constexpr int kLinMaxRows = 1024;
+// shared memory (elements of T): max over the tile shapes of staging (KC x (rows + 4) + KC x cols) and of the
+// output tile (rows x (cols + 1)) that aliases it
+constexpr int kLinSmemElems = 8832;
+
+template <typename T>
+__device__ __forceinline__ void lin_ld4(const T* p, T (&v)[4]);
+template <>
+__device__ __forceinline__ void lin_ld4<float>(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void lin_ld4<double>(const double* p, double (&v)[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
 
 struct LinParams {
   int num_blocks;
@@ -24,8 +41,9 @@ struct LinParams {
       dim[kLinMaxBlocks], w_off[kLinMaxBlocks];
   double scale[kLinMaxBlocks];
   int32_t cta_begin[kLinMaxBlocks + 1];  // prefix of CTA counts per block
-  int32_t col_chunks[kLinMaxBlocks];     // ceil(mul_out / kLinCols)
+  int32_t col_chunks[kLinMaxBlocks];     // ceil(mul_out / cols)
   int32_t nodes_per_tile[kLinMaxBlocks];
+  int32_t tile_cols[kLinMaxBlocks];      // 64 / 32 / 16 / 8 / 4: the tile is (4096 / cols) rows x cols
   int in_dim, out_dim, S;
   const void* x;
   const void* weight;
@@ -37,16 +55,13 @@ struct LinParams {
   int64_t N;
 };
 
+// Tile shape per block: narrow outputs (mul_out = 4 for the l = 2 irreps, 16 for l = 1) take tall tiles, so the
+// 4 x 4 register micro-kernel never multiplies padding (a fixed 64 x 64 tile spent 97 % of its instructions on
+// it for the l >= 1 blocks of lin2: ncu r1, 330 M instructions for 18 M useful FMAs).
 template <typename T>
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
-  // staging buffers; the output tile aliases them after the last k-chunk
-  constexpr int kStageElems = kLinK * (kLinRows + 4) + kLinK * kLinCols;
-  static_assert(kStageElems >= kLinRows * (kLinCols + 1), "output tile must fit in the staging buffers");
-  __shared__ __align__(16) unsigned char lin_smem[sizeof(T) * kStageElems];
-  T(*xsT)[kLinRows + 4] = reinterpret_cast<T(*)[kLinRows + 4]>(lin_smem);
-  T(*ws)[kLinCols] = reinterpret_cast<T(*)[kLinCols]>(lin_smem + sizeof(T) * kLinK * (kLinRows + 4));
-  T(*ot)[kLinCols + 1] = reinterpret_cast<T(*)[kLinCols + 1]>(lin_smem);
-  __shared__ int s_nodes[kLinRows];
+  extern __shared__ __align__(16) unsigned char lin_smem[];
+  __shared__ int s_nodes[kLinMaxRows];
 
   // which block / node tile / column chunk am I?
   int b = 0;
@@ -56,6 +71,12 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
   int tile = local / p.col_chunks[b];
   const int TN = p.nodes_per_tile[b];
   const int mi = p.mul_in[b], mo = p.mul_out[b], d = p.dim[b];
+  const int COLS = p.tile_cols[b], ROWS = kLinOut / COLS;
+  const int KC = min(32, kLinStage / ROWS);
+  const int XS = ROWS + 4;  // row stride of the transposed x stage
+  T* xsT = reinterpret_cast<T*>(lin_smem);              // [KC][XS]
+  T* ws = xsT + (size_t)KC * XS;                        // [KC][COLS]
+  T* ot = reinterpret_cast<T*>(lin_smem);               // [ROWS][COLS + 1], aliases the stage after the k loop
   // locate (species, tile-in-species)
   int s = 0;
   int64_t begin = 0, end = 0;
@@ -80,15 +101,14 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
   }
   const int tn = (int)(end - begin);
   const int tid = threadIdx.x;
-  if (tid < tn) s_nodes[tid] = p.sperm ? p.sperm[begin + tid] : (int)(begin + tid);
+  for (int t = tid; t < tn; t += blockDim.x) s_nodes[t] = p.sperm ? p.sperm[begin + t] : (int)(begin + t);
   __syncthreads();
 
   const T* __restrict__ X = static_cast<const T*>(p.x);
   const T* __restrict__ W = static_cast<const T*>(p.weight);
   T* __restrict__ OUT = static_cast<T*>(p.out);
-  const int c0 = cc * kLinCols;
-  const int ncols = min(kLinCols, mo - c0);
-  const int R = tn * d;
+  const int c0 = cc * COLS;
+  const int ncols = min(COLS, mo - c0);
 
   if (mi == 0) {  // irreps with no incoming path: zeros
     if (!p.accumulate) {
@@ -100,41 +120,45 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
     return;
   }
 
-  const int tc = tid & 15, tr = tid >> 4;
+  const int tcn = COLS >> 2;  // thread columns
+  const int tc = tid % tcn, tr = tid / tcn;
   T acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
 
-  for (int u0 = 0; u0 < mi; u0 += kLinK) {
-    const int ku = min(kLinK, mi - u0);
+  for (int u0 = 0; u0 < mi; u0 += KC) {
+    const int ku = min(KC, mi - u0);
     // stage weights  ws[uu][c] = W[w_off + ((u0+uu)*S + s)*mo + c0 + c]
-    for (int t = tid; t < kLinK * kLinCols; t += blockDim.x) {
-      int uu = t / kLinCols, c = t - uu * kLinCols;
+    for (int t = tid; t < KC * COLS; t += blockDim.x) {
+      int uu = t / COLS, c = t - uu * COLS;
       T v = T(0);
       if (uu < ku && c < ncols)
         v = p.transpose ? W[(size_t)p.w_off[b] + ((size_t)(c0 + c) * p.S + s) * mi + (u0 + uu)]
                         : W[(size_t)p.w_off[b] + ((size_t)(u0 + uu) * p.S + s) * mo + c0 + c];
-      ws[uu][c] = v;
+      ws[t] = v;
     }
-    // stage x transposed  xsT[uu][j*d+m] = X[node_j, in_off + (u0+uu)*d + m]
-    for (int t = tid; t < kLinRows * kLinK; t += blockDim.x) (&xsT[0][0])[(t / kLinRows) * (kLinRows + 4) + (t % kLinRows)] = T(0);
-    __syncthreads();
+    // stage x transposed  xsT[uu][j*d+m] = X[node_j, in_off + (u0+uu)*d + m]; rows beyond tn*d and uu >= ku are zero
     const int seg = ku * d;
+    const int R = tn * d;
+    if (ku < KC || R < ROWS) {  // partial chunk / tile only: the staging below overwrites everything else
+      for (int t = tid; t < KC * ROWS; t += blockDim.x) {
+        const int uu = t / ROWS, r = t - uu * ROWS;
+        if (uu >= ku || r >= R) xsT[uu * XS + r] = T(0);
+      }
+    }
     for (int t = tid; t < tn * seg; t += blockDim.x) {
       int j = t / seg, q = t - j * seg;
       int uu = q / d, m = q - uu * d;
-      xsT[uu][j * d + m] = X[(size_t)s_nodes[j] * p.in_dim + p.in_off[b] + u0 * d + q];
+      xsT[uu * XS + j * d + m] = X[(size_t)s_nodes[j] * p.in_dim + p.in_off[b] + u0 * d + q];
     }
     __syncthreads();
 #pragma unroll 4
-    for (int uu = 0; uu < kLinK; ++uu) {
+    for (int uu = 0; uu < KC; ++uu) {
       T a[4], bb[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = xsT[uu][tr * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bb[j] = ws[uu][tc * 4 + j];
+      lin_ld4<T>(xsT + uu * XS + tr * 4, a);   // 16-byte aligned: XS and COLS are multiples of 4
+      lin_ld4<T>(ws + uu * COLS + tc * 4, bb);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -143,10 +167,11 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
     __syncthreads();
   }
   const T scale = T(p.scale[b]);
+  const int OS = COLS + 1;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ot[tr * 4 + i][tc * 4 + j] = acc[i][j] * scale;
+    for (int j = 0; j < 4; ++j) ot[(tr * 4 + i) * OS + tc * 4 + j] = acc[i][j] * scale;
   __syncthreads();
   // coalesced write: per node the (w, m) range is contiguous
   const int span = ncols * d;
@@ -154,10 +179,9 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
     int j = t / span, q = t - j * span;
     int w = q / d, m = q - w * d;
     size_t o = (size_t)s_nodes[j] * p.out_dim + p.out_off[b] + c0 * d + q;
-    T v = ot[j * d + m][w];
+    T v = ot[(j * d + m) * OS + w];
     OUT[o] = p.accumulate ? (OUT[o] + v) : v;
   }
-  (void)R;
 }
 
 // =========================================================================
@@ -231,10 +255,14 @@ static int linear_fwd_round(int dtype, const mt_lin_block* const* blocks, int nu
     const mt_lin_block& k = *blocks[b];
     p.in_off[b] = k.in_off; p.out_off[b] = k.out_off; p.mul_in[b] = k.mul_in; p.mul_out[b] = k.mul_out;
     p.dim[b] = k.dim; p.w_off[b] = k.w_off; p.scale[b] = k.scale;
-    int tn = kLinRows / k.dim;
+    int cols = 64;
+    while (cols > 4 && cols / 2 >= k.mul_out) cols /= 2;  // smallest of 64/32/16/8/4 that covers mul_out (<= 64)
+    const int rows = kLinOut / cols;
+    int tn = rows / k.dim;
     if (tn < 1) tn = 1;
+    p.tile_cols[b] = cols;
     p.nodes_per_tile[b] = tn;
-    p.col_chunks[b] = ceil_div<int>(k.mul_out, kLinCols);
+    p.col_chunks[b] = ceil_div<int>(k.mul_out, cols);
     int64_t tiles = ceil_div<int64_t>(N, tn) + (species_ptr ? num_species : 0);
     p.cta_begin[b] = (int32_t)total;
     total += tiles * p.col_chunks[b];
@@ -245,7 +273,13 @@ static int linear_fwd_round(int dtype, const mt_lin_block* const* blocks, int nu
   p.x = x; p.weight = weight; p.sperm = species_perm; p.sptr = species_ptr;
   p.accumulate = accumulate; p.out = out; p.N = N;
   MT_DISPATCH_DTYPE(dtype, {
-    linear_fwd_kernel<T><<<(unsigned)total, 256, 0, st>>>(p);
+    const size_t smem = (size_t)kLinSmemElems * sizeof(T);
+    static thread_local bool configured = false;
+    if (!configured) {
+      MT_CUDA_OK(cudaFuncSetAttribute(linear_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    linear_fwd_kernel<T><<<(unsigned)total, 256, smem, st>>>(p);
   });
   MT_LAUNCH_OK();
   return MT_OK;
@@ -255,7 +289,7 @@ static int linear_check_blocks(const mt_lin_block* blocks, int num_blocks, int i
                                const void* weight) {
   for (int b = 0; b < num_blocks; ++b) {
     const mt_lin_block& k = blocks[b];
-    MT_REQUIRE(k.dim >= 1 && k.dim <= kLinRows && k.mul_out > 0 && k.mul_in >= 0, "bad linear block %d", b);
+    MT_REQUIRE(k.dim >= 1 && k.dim <= 64 && k.mul_out > 0 && k.mul_in >= 0, "bad linear block %d", b);
     MT_REQUIRE(k.out_off >= 0 && k.out_off + k.mul_out * k.dim <= out_dim, "block %d exceeds out_dim", b);
     MT_REQUIRE(k.mul_in == 0 || (k.in_off >= 0 && k.in_off + k.mul_in * k.dim <= in_dim), "block %d exceeds in_dim", b);
     MT_REQUIRE(k.mul_in == 0 || weight != nullptr, "null weight");
