@@ -1,0 +1,245 @@
+"""
+``predict()`` with the reference's signature (src/matten/predict.py:151-240) on the CUDA path.
+
+Differences a caller can see:
+  * structures may be pymatgen ``Structure`` objects (when pymatgen is installed) or plain dicts
+    ``{"lattice": 3x3, "species": [Z or symbol, ...], "coords": n x 3, "coords_are_cartesian": bool}``;
+  * elasticity tensors come back as ``pymatgen.analysis.elasticity.ElasticTensor`` only when pymatgen is
+    importable, otherwise as ``numpy`` arrays of shape [3,3,3,3];
+  * when ``torch.distributed`` is initialised with more than one rank, the structures are sharded over the ranks by
+    edge count (no data-path collective; one all-gather of the [B, 21] results at the end) and every rank returns the
+    full list.
+Everything else (species check with the reference's message, ``failed_entries`` -> ``None``, flat per-atom list
+for ``is_atomic_tensor``) follows the reference.
+"""
+from __future__ import annotations
+
+import io
+import os
+import pickle
+import warnings
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .data.neighbors import collate, make_graph, to_device
+from .model_factory.tfn_atomic_tensor import AtomicTensorModel
+from .model_factory.tfn_scalar_tensor import ScalarTensorModel
+from .nn.readout import CartesianTensorWrapper
+from .parallel import gather_predictions, shard_by_edges
+
+_SYMBOLS = ("H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr Rb Sr Y "
+            "Zr Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe Cs Ba La Ce Pr Nd Pm Sm Eu Gd Tb Dy Ho Er Tm Yb Lu Hf Ta W "
+            "Re Os Ir Pt Au Hg Tl Pb Bi Po At Rn Fr Ra Ac Th Pa U Np Pu Am Cm Bk Cf Es Fm Md No Lr").split()
+_Z_OF = {s: i + 1 for i, s in enumerate(_SYMBOLS)}
+
+
+# ------------------------------------------------------------------------------------------ structures
+def _structure_arrays(s) -> Dict[str, Any]:
+    """(lattice [3,3], cartesian coords [n,3], atomic numbers [n]) of a pymatgen Structure or a plain dict."""
+    if isinstance(s, dict):
+        lat = np.asarray(s["lattice"]["matrix"] if isinstance(s["lattice"], dict) else s["lattice"], dtype=np.float64)
+        if "atomic_numbers" in s:
+            Z = [int(z) for z in s["atomic_numbers"]]
+        elif "species" in s:
+            Z = [int(z) if not isinstance(z, str) else _Z_OF[z] for z in s["species"]]
+        else:  # pymatgen Structure.as_dict(): sites with species lists
+            Z = [_Z_OF[site["species"][0]["element"]] for site in s["sites"]]
+        if "cart_coords" in s:
+            cart = np.asarray(s["cart_coords"], dtype=np.float64)
+        elif "sites" in s and "coords" not in s:
+            cart = np.asarray([site["xyz"] for site in s["sites"]], dtype=np.float64)
+        else:
+            c = np.asarray(s["coords"], dtype=np.float64)
+            cart = c if s.get("coords_are_cartesian", False) else c @ lat
+        return {"lattice": lat.reshape(3, 3), "cart": cart.reshape(-1, 3), "Z": Z}
+    # duck-typed pymatgen Structure
+    return {"lattice": np.asarray(s.lattice.matrix, dtype=np.float64),
+            "cart": np.asarray(s.cart_coords, dtype=np.float64),
+            "Z": [int(z) for z in s.atomic_numbers]}
+
+
+def check_species(model, structures: Sequence[Dict[str, Any]]):
+    """reference src/matten/predict.py:96-114"""
+    supported = set(model.hparams["dataset_hparams"]["allowed_species"])
+    for i, s in enumerate(structures):
+        numbers = set(s["Z"])
+        if not numbers.issubset(supported):
+            bad = ", ".join(f"{_SYMBOLS[n - 1] if 0 < n <= len(_SYMBOLS) else '?'} ({n})"
+                            for n in sorted(numbers - supported))
+            raise RuntimeError(f"Cannot make predictions for structure {i}. It contains species {bad} not supported "
+                               f"by the model. The model were trained with species {supported}.")
+
+
+# ------------------------------------------------------------------------------------------ checkpoints
+class _Stub:
+    """Placeholder for classes of packages that are not installed (pytorch_lightning, torchmetrics, matten, ...)
+    referenced inside a Lightning checkpoint; only tensors and plain containers are read from it."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {"state": state})
+
+
+class _TolerantUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        try:
+            return super().find_class(module, name)
+        except Exception:
+            return type(name, (_Stub,), {"__module__": module})
+
+
+class _TolerantPickle:
+    Unpickler = _TolerantUnpickler
+    __name__ = "tolerant_pickle"
+
+    @staticmethod
+    def load(f, **kw):
+        return _TolerantUnpickler(f, **kw).load()
+
+
+def load_checkpoint(path: Union[str, os.PathLike]) -> Dict[str, Any]:
+    """Lightning ``.ckpt`` (or a plain ``{"state_dict", "hyper_parameters"}`` / state_dict file) -> dict with
+    ``state_dict`` and ``hyper_parameters``; classes of packages that are not installed unpickle as stubs."""
+    try:
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+    except Exception:
+        ck = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_TolerantPickle)
+    if "state_dict" not in ck:
+        ck = {"state_dict": ck, "hyper_parameters": {}}
+    return ck
+
+
+def get_pretrained_model_dir(identifier: str) -> Path:
+    p = Path(identifier)
+    if p.exists() and p.is_dir():
+        return p
+    return Path(__file__).resolve().parent.parent / "pretrained" / identifier
+
+
+def get_pretrained_config(identifier: str, config_filename: str = "config_final.yaml") -> Dict[str, Any]:
+    import yaml
+
+    with open(get_pretrained_model_dir(identifier) / config_filename) as f:
+        return yaml.safe_load(f)
+
+
+def get_pretrained_model(identifier: str, checkpoint: str = "model_final.ckpt", model_class=ScalarTensorModel,
+                         device=None):
+    """``model_class.load_from_checkpoint`` of the reference: hyper-parameters and weights from the checkpoint (the
+    backbone section of ``config_final.yaml`` is the fallback when the checkpoint carries no hyper-parameters)."""
+    directory = get_pretrained_model_dir(identifier)
+    ck = load_checkpoint(directory / checkpoint)
+    hp = ck.get("hyper_parameters") or {}
+    backbone = hp.get("backbone_hparams")
+    dataset = hp.get("dataset_hparams")
+    if backbone is None:
+        backbone = get_pretrained_config(identifier)["model"]
+    if dataset is None:
+        raise RuntimeError("the checkpoint holds no dataset_hparams (allowed_species); cannot build the model")
+    model = model_class(dict(backbone), dict(dataset))
+    sd = {k: v for k, v in ck["state_dict"].items() if not k.startswith("metrics.")}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    missing = [k for k in missing]
+    # e3nn modules store constant buffers (w3j tables, output masks) that this implementation regenerates
+    unexpected = [k for k in unexpected if not any(t in k for t in ("_w3j", "output_mask", "num_batches_tracked"))]
+    if missing or unexpected:
+        raise RuntimeError(f"checkpoint does not match the model: missing {missing[:5]}, unexpected {unexpected[:5]}")
+    if device is not None:
+        model = model.to(device)
+    return model.eval()
+
+
+# ------------------------------------------------------------------------------------------ evaluation
+def _graphs(structs: Sequence[Dict[str, Any]], r_cut: float, dtype):
+    graphs, failed = [], []
+    for i, s in enumerate(structs):
+        try:  # reference dataset/structure_scalar_tensor.py:357-362: failed conversions are skipped
+            graphs.append(make_graph(s["cart"], s["lattice"], s["Z"], r_cut, dtype=dtype))
+        except Exception as e:  # noqa: BLE001
+            warnings.warn(f"Failed converting structure {i}: {e}. Skip it.")
+            failed.append(i)
+    return graphs, failed
+
+
+def evaluate(model, graphs: List[Dict[str, torch.Tensor]], batch_size: int, device, tensor_target_name: str,
+             tensor_target_formula: str = "ijkl=jikl=klij") -> List[torch.Tensor]:
+    """reference src/matten/predict.py:117-148: batches of ``batch_size`` graphs, irreps -> Cartesian."""
+    converter = CartesianTensorWrapper(tensor_target_formula)
+    out: List[torch.Tensor] = []
+    model.eval()
+    with torch.no_grad():
+        for i in range(0, len(graphs), batch_size):
+            batch = to_device(collate(graphs[i:i + batch_size]), device)
+            p = model(batch)[tensor_target_name]
+            out.extend(converter.to_cartesian(p).cpu())
+    return out
+
+
+def predict(structure, model_identifier="20230627", checkpoint: str = "model_final.ckpt", batch_size: int = 200,
+            logger_level: str = "ERROR", is_elasticity_tensor: bool = True, is_atomic_tensor: bool = False,
+            device: Optional[Union[str, torch.device]] = None):
+    """Predict the tensor property of a structure or a list of structures (see the module docstring)."""
+    single = not isinstance(structure, (list, tuple))
+    structs = [_structure_arrays(s) for s in ([structure] if single else structure)]
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("matten_b200.predict needs a CUDA device (there is no CPU fallback)")
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if is_atomic_tensor:
+        model_class, is_elasticity_tensor = AtomicTensorModel, False
+    else:
+        model_class = ScalarTensorModel
+    model = get_pretrained_model(model_identifier, checkpoint, model_class, device)
+    check_species(model, structs)
+    config = get_pretrained_config(model_identifier)
+    name = config["data"]["tensor_target_name"]
+    formula = config["data"]["tensor_target_formula"]
+    model.task_name = name
+    dtype = next(model.parameters()).dtype
+    graphs, failed = _graphs(structs, float(config["data"]["r_cut"]), dtype)
+
+    dist = torch.distributed
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if world > 1 and not is_atomic_tensor:
+        shards = shard_by_edges([int(g["edge_index"].shape[1]) for g in graphs], world)
+        mine = shards[dist.get_rank()]
+        local = evaluate(model, [graphs[i] for i in mine], batch_size, device, name, formula)
+        flat = (torch.stack(local).reshape(len(local), -1) if local else
+                torch.zeros((0, 3 ** len(formula.split("=")[0])), dtype=dtype)).to(device)
+        allp = gather_predictions(flat, [len(s) for s in shards]).cpu()
+        predictions = list(allp.reshape((allp.shape[0],) + (3,) * len(formula.split("=")[0])))
+    else:
+        predictions = evaluate(model, graphs, batch_size, device, name, formula)
+
+    if is_elasticity_tensor:
+        try:
+            from pymatgen.analysis.elasticity import ElasticTensor
+
+            predictions = [ElasticTensor(t.numpy()) for t in predictions]
+        except ImportError:
+            predictions = [t.numpy() for t in predictions]
+    else:
+        predictions = [t.numpy() for t in predictions]
+
+    if failed and not is_atomic_tensor:
+        it = iter(predictions)
+        fs = set(failed)
+        predictions = [None if i in fs else next(it) for i in range(len(structs))]
+        warnings.warn("Cannot make predictions for the following structures. Their returned elasticity tensor set "
+                      f"to `None`: {sorted(fs)}.")
+    if single and not is_atomic_tensor:
+        return predictions[0]
+    return predictions
+
+
+def save_checkpoint(model, path: Union[str, os.PathLike]):
+    """Write ``{"state_dict", "hyper_parameters"}`` in the layout of the reference's Lightning checkpoints (keys
+    ``backbone.*`` / ``extra_layers_dict.*``), so that either implementation can load the other's weights."""
+    torch.save({"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
+                "hyper_parameters": dict(model.hparams)}, path)
