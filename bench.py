@@ -183,6 +183,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")  # the version banner goes to stdout; rank 0 must print ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
@@ -196,16 +198,28 @@ def run_ours(args):
     resident = {k: v.to(dev) for k, v in pinned.items()}
     resident["num_graphs"] = B
 
+    from matten_b200.graphs import CapturedForward
+
+    captured = None if args.no_cuda_graph else CapturedForward(model)
+
     def step_resident():
+        if captured is not None:
+            return captured(resident, check=False)["elastic_tensor_full"]
         return model(resident, check=False)["elastic_tensor_full"]
 
     out_host = torch.empty((B, 6), dtype=torch.float32).pin_memory()
     d2h_bytes = out_host.numel() * out_host.element_size()
 
     def step_e2e():
-        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        d["num_graphs"] = B
-        out = model(d, check=True)["elastic_tensor_full"]  # reads the device error word (one sync)
+        if captured is not None:
+            static = captured.static_inputs(resident)
+            for k, v in pinned.items():
+                static[k].copy_(v, non_blocking=True)  # pinned host -> the graph's input buffers
+            out = captured(static, check=True)["elastic_tensor_full"]  # reads the device error word (one sync)
+        else:
+            d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+            d["num_graphs"] = B
+            out = model(d, check=True)["elastic_tensor_full"]
         out_host.copy_(out, non_blocking=True)
         return out
 
@@ -230,19 +244,29 @@ def run_ours(args):
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        ops.CONV_EVENTS = []
-        l0 = ops.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(args.steps):
             out = step_resident()
         ev1.record()
         barrier()
-        launches = ops.launch_count() - l0
         ms_res = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        assert torch.isfinite(out).all()
+        # per-kernel view of the same step: a CUDA graph replay cannot carry per-kernel events and does not pass
+        # through the library's launch counter, so the conv durations (CUDA events around each mt_conv_fwd on the
+        # launching stream) and the launch count come from K kernel-by-kernel steps of the identical forward
+        ops.CONV_EVENTS = []
+        l0 = ops.launch_count()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        for _ in range(args.steps):
+            model(resident, check=False)
+        ev3.record()
+        barrier()
+        launches = ops.launch_count() - l0
+        ms_eager = max_over_ranks(ev2.elapsed_time(ev3) / args.steps)
         conv_events = ops.CONV_EVENTS
         ops.CONV_EVENTS = None
-        assert torch.isfinite(out).all()
         # ---------------- end to end (pinned host -> device -> host) ----------------
         for _ in range(min(args.warmup, 3)):
             step_e2e()
@@ -331,6 +355,10 @@ def run_ours(args):
                     "ms_per_step": round(ms_e2e, 4), "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches), "launches_per_step": round(launches / args.steps, 1),
+            "launch_mode": ("kernel by kernel" if captured is None else
+                            "CUDA graph replay of the forward (one capture per batch shape); gpu_launches counted on "
+                            "the same number of kernel-by-kernel steps"),
+            "ms_per_step_kernel_by_kernel": round(ms_eager, 4),
             "roofline": roofline, "clocks": clocks, "train": train,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -350,6 +378,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="launch the forward kernel by kernel from Python")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -95,6 +95,7 @@ class _TensorModelBase(torch.nn.Module):
         target transform; the shipped configs use no normaliser)."""
         d = self.preprocess(data)
         preds = self.decode(d)
+        self._last_graph = d.get(K.GRAPH_CACHE)  # index bookkeeping + device error word of this forward
         if check and K.GRAPH_CACHE in d:
             d[K.GRAPH_CACHE].raise_if_invalid()
         return preds
