@@ -16,7 +16,7 @@ static int pad_hp_bwd(int h) {
 struct BwdLayout {
   size_t z_off[MT_MAX_MLP_LAYERS];
   size_t dw_off, dxe_off, dhp_off, partl_off, parth_off, total;
-  int ncg, grid2, grid3, hid_numel;
+  int ncg, grid2, grid3, hid_numel, hid_eb, rs;
 };
 
 static BwdLayout bwd_layout(const mt_conv_plan* plan, size_t es, int64_t E) {
@@ -35,7 +35,12 @@ static BwdLayout bwd_layout(const mt_conv_plan* plan, size_t es, int64_t E) {
   L.ncg = ceil_div<int>(Wn, kLastCW);
   const int64_t chunks2 = ceil_div<int64_t>(E, kLastEB);
   L.grid2 = (int)(chunks2 < 2 * kNumSMs ? (chunks2 > 0 ? chunks2 : 1) : 2 * kNumSMs);
-  const int64_t chunks3 = ceil_div<int64_t>(E, kHidEB);
+  int hmax = 1;
+  for (int i = 0; i < nl; ++i) hmax = plan->mlp_sizes[i] > hmax ? plan->mlp_sizes[i] : hmax;
+  L.rs = hmax + 1;
+  L.hid_eb = kHidEBMax;
+  while (L.hid_eb > 16 && ((size_t)3 * L.hid_eb * L.rs + (size_t)L.rs * L.rs + hid) * es > 72 * 1024) L.hid_eb >>= 1;
+  const int64_t chunks3 = ceil_div<int64_t>(E, L.hid_eb);
   L.grid3 = (int)(chunks3 < 2 * kNumSMs ? (chunks3 > 0 ? chunks3 : 1) : 2 * kNumSMs);
   L.dw_off = o;
   o += align256((size_t)E * Wn * es);
@@ -99,16 +104,18 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
   p.xs_stride = p.x_dim | 1;
   p.hs_stride = (H + 3) / 4 * 4;
   p.wt_stride = Wn;
+  p.rs = L.rs;
+  p.hid_eb = L.hid_eb;
 
   // K0: hidden pre-activations
   if (nl > 1) {
-    const size_t smem0 = ((size_t)kHidEB * (kBwdMaxH + 1) + (size_t)kBwdMaxH * kBwdMaxH) * sizeof(T);
-    static thread_local bool cfg0 = false;
-    if (!cfg0) {
+    const size_t smem0 = ((size_t)p.hid_eb * p.rs + (size_t)p.rs * p.rs) * sizeof(T);
+    static thread_local size_t cfg0 = 0;
+    if (smem0 > cfg0) {
       MT_CUDA_OK(cudaFuncSetAttribute(edge_hidden_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-      cfg0 = true;
+      cfg0 = smem0;
     }
-    const int64_t chunks = ceil_div<int64_t>(E, kHidEB);
+    const int64_t chunks = ceil_div<int64_t>(E, p.hid_eb);
     const int grid0 = (int)(chunks < 4 * kNumSMs ? chunks : 4 * kNumSMs);
     edge_hidden_kernel<T><<<grid0, 256, smem0, st>>>(p);
     MT_LAUNCH_OK();
@@ -124,7 +131,8 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
       if (TN < 1) TN = 1;
       if (TN > 16) TN = 16;
       for (;;) {
-        smem = fixed + ((size_t)EC * (p.hs_stride + p.xs_stride + p.y_dim + p.wt_stride) + (size_t)TN * p.out_dim) * sizeof(T);
+        smem = fixed + ((size_t)EC * (p.hs_stride + p.xs_stride + p.y_dim + p.wt_stride) + (size_t)TN * (p.out_dim + 1)) * sizeof(T) +
+               (size_t)EC * sizeof(int);
         if (smem <= 110 * 1024 || TN == 1) break;
         TN = TN / 2;
       }
@@ -167,7 +175,7 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
       MT_LAUNCH_OK();
     }
     if (nl > 1) {
-      const size_t smem3 = ((size_t)3 * kHidEB * (kBwdMaxH + 1) + (size_t)kBwdMaxH * (kBwdMaxH + 1) + p.hid_numel) * sizeof(T);
+      const size_t smem3 = ((size_t)3 * p.hid_eb * p.rs + (size_t)p.rs * p.rs + p.hid_numel) * sizeof(T);
       MT_REQUIRE(smem3 <= 227 * 1024, "hidden MLP too large for the backward kernel");
       static thread_local size_t cfg3 = 0;
       if (smem3 > cfg3) {

@@ -26,7 +26,7 @@ constexpr int kBwdMaxH = 64;     // largest MLP layer input/hidden size the back
 constexpr int kBwdET = 8;        // edges per register pass of phase A (chunk_edges is a multiple of it)
 constexpr int kLastEB = 64;      // edges per chunk of K2
 constexpr int kLastCW = 128;     // weight columns per CTA column group of K2
-constexpr int kHidEB = 64;       // edges per chunk of K0 / K3
+constexpr int kHidEBMax = 128;   // edges per chunk of K0 / K3 (halved until the tiles fit: ConvBwdParams::hid_eb)
 
 struct ConvBwdParams {
   int x_dim, y_dim, out_dim, Wn;
@@ -57,6 +57,8 @@ struct ConvBwdParams {
   int64_t N, E;
   int tile_nodes, chunk_edges, xs_stride, hs_stride, wt_stride;
   int ncg, grid2, grid3, hid_numel;
+  int hid_eb;  // edges per chunk of K0 / K3
+  int rs;  // row stride of the per-edge activation tiles of K0 / K3: largest input / hidden size + 1
 };
 
 template <typename T>
@@ -85,18 +87,19 @@ __device__ __forceinline__ T last_input(const ConvBwdParams& p, int64_t e, int k
 template <typename T>
 __global__ void __launch_bounds__(256) edge_hidden_kernel(const ConvBwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* A = reinterpret_cast<T*>(smem_raw);               // [kHidEB][kBwdMaxH + 1]
-  T* Wl = A + (size_t)kHidEB * (kBwdMaxH + 1);         // [<=64][<=64] of the current layer, pre-scaled
+  const int RS = p.rs, EB = p.hid_eb;
+  T* A = reinterpret_cast<T*>(smem_raw);               // [EB][RS]
+  T* Wl = A + (size_t)EB * RS;                     // [<=64][<=64] of the current layer, pre-scaled
   const int tid = threadIdx.x;
-  const int64_t nchunks = ceil_div<int64_t>(p.E, kHidEB);
+  const int64_t nchunks = ceil_div<int64_t>(p.E, EB);
   for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const int64_t e0 = ch * kHidEB;
-    const int ne = (int)imin64(kHidEB, p.E - e0);
+    const int64_t e0 = ch * EB;
+    const int ne = (int)imin64(EB, p.E - e0);
     const int in0 = p.sizes[0];
     __syncthreads();
     for (int t = tid; t < ne * in0; t += blockDim.x) {
       const int el = t / in0, k = t - el * in0;
-      A[el * (kBwdMaxH + 1) + k] = static_cast<const T*>(p.emb)[(size_t)p.perm[e0 + el] * in0 + k];
+      A[el * RS + k] = static_cast<const T*>(p.emb)[(size_t)p.perm[e0 + el] * in0 + k];
     }
     for (int l = 0; l + 1 < p.nl; ++l) {
       const int fi = p.sizes[l], fo = p.sizes[l + 1];
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(256) edge_hidden_kernel(const ConvBwdParams p)
       T* Z = static_cast<T*>(p.z[l]);
       for (int t = tid; t < ne * fo; t += blockDim.x) {
         const int el = t / fo, j = t - el * fo;
-        const T* ar = A + el * (kBwdMaxH + 1);
+        const T* ar = A + el * RS;
         T acc = T(0);
         for (int k = 0; k < fi; ++k) acc = fma(ar[k], Wl[k * fo + j], acc);
         Z[(size_t)(e0 + el) * fo + j] = acc;
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(256) edge_hidden_kernel(const ConvBwdParams p)
       // every thread re-reads the entries it wrote itself (same t mapping): no fence needed
       for (int t = tid; t < ne * fo; t += blockDim.x) {
         const int el = t / fo, j = t - el * fo;
-        A[el * (kBwdMaxH + 1) + j] = apply_act<T>(p.act, Z[(size_t)(e0 + el) * fo + j]) * T(p.act_cst);
+        A[el * RS + j] = apply_act<T>(p.act, Z[(size_t)(e0 + el) * fo + j]) * T(p.act_cst);
       }
       __syncthreads();
     }
@@ -127,8 +130,9 @@ __global__ void __launch_bounds__(256) edge_hidden_kernel(const ConvBwdParams p)
 template <typename T, int L1>
 __device__ __forceinline__ void bwd_unit(const ConvBwdParams& p, const int4* __restrict__ spath, int pfirst, int pcount,
                                          int u, int xoff, const T* __restrict__ xs, const T* __restrict__ ys,
-                                         const T* __restrict__ wt, const T* __restrict__ gs, int el0, int el1,
-                                         int phase, int nphase, int c0, T inv_den) {
+                                         const T* __restrict__ wt, const T* __restrict__ gs,
+                                         const int* __restrict__ enode, const T* __restrict__ sden, int el0, int el1,
+                                         int phase, int nphase, int c0) {
   constexpr int D1 = 2 * L1 + 1;
   T* __restrict__ DW = static_cast<T*>(p.DW);
   T* __restrict__ DXE = static_cast<T*>(p.DXE);
@@ -140,6 +144,9 @@ __device__ __forceinline__ void bwd_unit(const ConvBwdParams& p, const int4* __r
     for (int m = 0; m < D1; ++m) { xv[m] = xr[m]; dxv[m] = T(0); }
     const T* wrow = wt + (size_t)el * p.wt_stride;
     const T* yrow = ys + (size_t)el * p.y_dim;
+    const int nl_ = enode[el];  // receiver of this edge within the tile
+    const T* gn = gs + (size_t)nl_ * p.out_dim;
+    const T inv_den = sden[nl_];
     T* dwrow = DW + (size_t)(c0 + el) * p.Wn;
     for (int pk = 0; pk < pcount; ++pk) {
       const int4 pt = spath[pfirst + pk];  // {type, weight column of u = 0, sh offset, out offset of u = 0}
@@ -152,7 +159,7 @@ __device__ __forceinline__ void bwd_unit(const ConvBwdParams& p, const int4* __r
       constexpr int D2 = 2 * B + 1, D3 = 2 * C + 1;                \
       T yv[D2], gv[D3];                                            \
       _Pragma("unroll") for (int m = 0; m < D2; ++m) yv[m] = yrow[pt.z + m]; \
-      const T* gr = gs + pt.w + u * D3;                            \
+      const T* gr = gn + pt.w + u * D3;                            \
       _Pragma("unroll") for (int m = 0; m < D3; ++m) gv[m] = gr[m]; \
       dwrow[c] = CG<A, B, C>::template dot<T>(xv, yv, gv) * inv_den; \
       CG<A, B, C>::template bwd_x<T>(yv, gv, w, dxv);              \
@@ -179,6 +186,8 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(const ConvBwdParams p)
   T* ys = xs + (size_t)EC * p.xs_stride;               // [EC][y_dim]
   T* wt = ys + (size_t)EC * p.y_dim;                   // [EC][wt_stride]
   T* gs = wt + (size_t)EC * p.wt_stride;               // [tile_nodes][out_dim]
+  T* sden = gs + (size_t)p.tile_nodes * p.out_dim;     // [tile_nodes] 1 / sqrt(#neighbours)
+  int* enode = reinterpret_cast<int*>(sden + p.tile_nodes);  // [EC] receiver (tile-local) of every staged edge
   __shared__ int s_counter;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -202,6 +211,10 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(const ConvBwdParams p)
     __syncthreads();
     // grad_out rows of the tile's nodes
     for (int t = tid; t < tn * p.out_dim; t += blockDim.x) gs[t] = G[(size_t)n0 * p.out_dim + t];
+    for (int t = tid; t < tn; t += blockDim.x) {
+      const T den = p.num_neigh ? sqrt(static_cast<const T*>(p.num_neigh)[n0 + t]) : sqrt(T(p.avg));
+      sden[t] = T(1) / den;
+    }
     for (int c0 = e_begin; c0 < e_end; c0 += EC) {
       const int c1 = min(c0 + EC, e_end);
       const int ne = c1 - c0;
@@ -220,6 +233,11 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(const ConvBwdParams p)
       for (int t = tid; t < EC * H; t += blockDim.x) {
         const int k = t / EC, el = t - k * EC;  // lanes walk the edges: conflict-free stores
         hs[(size_t)k * EC + el] = (el < ne) ? last_input<T>(p, (int64_t)c0 + el, k) * inv_sqrt_h : T(0);
+      }
+      for (int el = tid; el < ne; el += blockDim.x) {
+        int j = 0;
+        while (j + 1 < tn && p.rowptr[n0 + j + 1] <= c0 + el) ++j;
+        enode[el] = j;
       }
       if (tid == 0) s_counter = 0;
       __syncthreads();
@@ -254,32 +272,28 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(const ConvBwdParams p)
         }
       }
       __syncthreads();
-      // ------------------------------------------------------------ (B) units
-      const int num_units = p.num_items * tn;
+      // ------------------------------------------------------------ (B) units: (item, block of 8 staged edges).
+      // The outputs are per edge, so a unit need not be a whole node: small units keep the 8 warps balanced.
+      const int nblk = (ne + 7) >> 3;
+      const int num_units = p.num_items * nblk;
       while (true) {
         int unit = 0;
         if (lane == 0) unit = atomicAdd(&s_counter, 1);
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= num_units) break;
-        const int item = unit / tn;
-        const int nl_ = unit - item * tn;
-        const int64_t n = n0 + nl_;
+        const int item = unit / nblk;
+        const int eb = unit - item * nblk;
         const int4 hdr = reinterpret_cast<const int4*>(p.item_hdr)[item];  // {l1, cpw, first path, count}
         const int2 ls = reinterpret_cast<const int2*>(p.lane_tab)[item * 32 + lane];
         const int cpw = hdr.y;
         const int phase = lane / cpw, nphase = 32 / cpw;
-        const int r0 = p.rowptr[n], r1 = p.rowptr[n + 1];
-        const int lo = max(r0, c0), hi = min(r1, c1);
-        if (lo >= hi) continue;
-        const T den = p.num_neigh ? sqrt(static_cast<const T*>(p.num_neigh)[n]) : sqrt(T(p.avg));
-        const T inv_den = T(1) / den;
-        const T* gn = gs + (size_t)nl_ * p.out_dim;
+        const int lo = eb * 8, hi = min(lo + 8, ne);
         switch (hdr.x) {
-          case 0: bwd_unit<T, 0>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gn, lo - c0, hi - c0, phase, nphase, c0, inv_den); break;
-          case 1: bwd_unit<T, 1>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gn, lo - c0, hi - c0, phase, nphase, c0, inv_den); break;
-          case 2: bwd_unit<T, 2>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gn, lo - c0, hi - c0, phase, nphase, c0, inv_den); break;
-          case 3: bwd_unit<T, 3>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gn, lo - c0, hi - c0, phase, nphase, c0, inv_den); break;
-          case 4: bwd_unit<T, 4>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gn, lo - c0, hi - c0, phase, nphase, c0, inv_den); break;
+          case 0: bwd_unit<T, 0>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gs, enode, sden, lo, hi, phase, nphase, c0); break;
+          case 1: bwd_unit<T, 1>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gs, enode, sden, lo, hi, phase, nphase, c0); break;
+          case 2: bwd_unit<T, 2>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gs, enode, sden, lo, hi, phase, nphase, c0); break;
+          case 3: bwd_unit<T, 3>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gs, enode, sden, lo, hi, phase, nphase, c0); break;
+          case 4: bwd_unit<T, 4>(p, spath, hdr.z, hdr.w, ls.x, ls.y, xs, ys, wt, gs, enode, sden, lo, hi, phase, nphase, c0); break;
           default: break;
         }
       }
@@ -384,23 +398,23 @@ __global__ void __launch_bounds__(256) mlp_bwd_last_kernel(const ConvBwdParams p
 // ---------------------------------------------------------------------------------------------- K3
 template <typename T>
 __global__ void __launch_bounds__(256) mlp_bwd_hidden_kernel(const ConvBwdParams p) {
-  constexpr int RS = kBwdMaxH + 1;
+  const int RS = p.rs, EB = p.hid_eb;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* DA = reinterpret_cast<T*>(smem_raw);   // [kHidEB][RS]  gradient w.r.t. the layer's output activation
-  T* DZ = DA + (size_t)kHidEB * RS;         // [kHidEB][RS]
-  T* A = DZ + (size_t)kHidEB * RS;          // [kHidEB][RS]  the layer's input activation
-  T* Wl = A + (size_t)kHidEB * RS;          // [<=64][fo + 1] current layer, pre-scaled (padded: lanes walk k)
-  T* accW = Wl + (size_t)kBwdMaxH * RS;     // [hid_numel] running partial sums of this CTA
+  T* DA = reinterpret_cast<T*>(smem_raw);   // [EB][RS]  gradient w.r.t. the layer's output activation
+  T* DZ = DA + (size_t)EB * RS;         // [EB][RS]
+  T* A = DZ + (size_t)EB * RS;          // [EB][RS]  the layer's input activation
+  T* Wl = A + (size_t)EB * RS;          // [<=64][fo + 1] current layer, pre-scaled (padded: lanes walk k)
+  T* accW = Wl + (size_t)(RS - 1) * RS;     // [hid_numel] running partial sums of this CTA
   const int tid = threadIdx.x;
   for (int t = tid; t < p.hid_numel; t += blockDim.x) accW[t] = T(0);
   const int H = p.sizes[p.nl - 1];
-  const int64_t nchunks = ceil_div<int64_t>(p.E, kHidEB);
+  const int64_t nchunks = ceil_div<int64_t>(p.E, EB);
   for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const int64_t e0 = ch * kHidEB;
-    const int ne = (int)imin64(kHidEB, p.E - e0);
+    const int64_t e0 = ch * EB;
+    const int ne = (int)imin64(EB, p.E - e0);
     __syncthreads();
     // da_{nl-1}: fixed-order sum of the column-group partials of K2
-    for (int t = tid; t < kHidEB * H; t += blockDim.x) {
+    for (int t = tid; t < EB * H; t += blockDim.x) {
       const int el = t / H, k = t - el * H;
       T s = T(0);
       if (el < ne)
@@ -416,13 +430,13 @@ __global__ void __launch_bounds__(256) mlp_bwd_hidden_kernel(const ConvBwdParams
       __syncthreads();
       for (int t = tid; t < fi * fo; t += blockDim.x) Wl[(t / fo) * (fo + 1) + (t % fo)] = Wg[t] * s;
       const T* Z = static_cast<const T*>(p.z[l]);
-      for (int t = tid; t < kHidEB * fo; t += blockDim.x) {
+      for (int t = tid; t < EB * fo; t += blockDim.x) {
         const int el = t / fo, j = t - el * fo;
         T v = T(0);
         if (el < ne) v = DA[el * RS + j] * apply_act_grad<T>(p.act, Z[(size_t)(e0 + el) * fo + j]) * T(p.act_cst);
         DZ[el * RS + j] = v;
       }
-      for (int t = tid; t < kHidEB * fi; t += blockDim.x) {
+      for (int t = tid; t < EB * fi; t += blockDim.x) {
         const int el = t / fi, k = t - el * fi;
         T v = T(0);
         if (el < ne) {
@@ -436,13 +450,13 @@ __global__ void __launch_bounds__(256) mlp_bwd_hidden_kernel(const ConvBwdParams
       for (int t = tid; t < fi * fo; t += blockDim.x) {
         const int k = t / fo, j = t - k * fo;
         T acc = T(0);
-        for (int el = 0; el < kHidEB; ++el) acc = fma(A[el * RS + k], DZ[el * RS + j], acc);
+        for (int el = 0; el < EB; ++el) acc = fma(A[el * RS + k], DZ[el * RS + j], acc);
         accW[woff + t] += acc;
       }
       __syncthreads();
       if (l > 0) {
         // da_l[e][k] = sum_j DZ[e][j] W_l[k][j] / sqrt(fi)
-        for (int t = tid; t < kHidEB * fi; t += blockDim.x) {
+        for (int t = tid; t < EB * fi; t += blockDim.x) {
           const int el = t / fi, k = t - el * fi;
           T acc = T(0);
           for (int j = 0; j < fo; ++j) acc = fma(DZ[el * RS + j], Wl[k * (fo + 1) + j], acc);
