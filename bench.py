@@ -210,17 +210,45 @@ def run_ours(args):
     out_host = torch.empty((B, 6), dtype=torch.float32).pin_memory()
     d2h_bytes = out_host.numel() * out_host.element_size()
 
-    def step_e2e():
-        if captured is not None:
-            static = captured.static_inputs(resident)
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0, "primed": False}
+
+    def _issue_copy(slot):
+        """pinned host -> the input buffers of graph `slot`, on the copy stream (overlaps the previous step's kernels)"""
+        static = captured.static_inputs(resident, slot)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_done[slot])  # the step that last used these buffers has finished
             for k, v in pinned.items():
-                static[k].copy_(v, non_blocking=True)  # pinned host -> the graph's input buffers
-            out = captured(static, check=True)["elastic_tensor_full"]  # reads the device error word (one sync)
+                static[k].copy_(v, non_blocking=True)
+            ev_copied[slot].record(copy_stream)
+        return static
+
+    def step_e2e():
+        """One end-to-end step: H2D of this step's inputs, forward, D2H of the result, device error word checked.
+        Steps are double buffered: the H2D of step i+1 is issued before step i's kernels, so it overlaps them; every
+        step still pays for its own copy inside the timed region."""
+        if captured is not None:
+            i = e2e_state["i"]
+            slot = i & 1
+            if not e2e_state["primed"]:
+                _issue_copy(slot)
+                e2e_state["primed"] = True
+            _issue_copy(slot ^ 1)  # next step's inputs
+            static = captured.static_inputs(resident, slot)
+            torch.cuda.current_stream(dev).wait_event(ev_copied[slot])
+            out = captured(static, check=False, slot=slot)["elastic_tensor_full"]
+            out_host.copy_(out, non_blocking=True)
+            ev_done[slot].record(torch.cuda.current_stream(dev))
+            torch.cuda.current_stream(dev).synchronize()  # the result is on the host: one sync per step
+            ops.raise_on_flag(captured.error_flag(resident, slot))
+            e2e_state["i"] = i + 1
         else:
             d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
             d["num_graphs"] = B
             out = model(d, check=True)["elastic_tensor_full"]
-        out_host.copy_(out, non_blocking=True)
+            out_host.copy_(out, non_blocking=True)
         return out
 
     def barrier():

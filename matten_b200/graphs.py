@@ -23,9 +23,9 @@ class CapturedForward:
         self._graphs: Dict[Tuple, tuple] = {}
 
     @staticmethod
-    def _signature(batch) -> Tuple:
-        return tuple(sorted((k, tuple(v.shape), str(v.dtype)) if isinstance(v, torch.Tensor) else (k, v)
-                            for k, v in batch.items() if not k.startswith("_")))
+    def _signature(batch, slot: int = 0) -> Tuple:
+        return (slot,) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) if isinstance(v, torch.Tensor) else (k, v)
+                                      for k, v in batch.items() if not k.startswith("_")))
 
     def _capture(self, batch):
         dev = next(self.model.parameters()).device
@@ -46,10 +46,11 @@ class CapturedForward:
             flag = last.flag if last is not None else None  # zeroed by a captured fill at every replay
         return g, static, out, flag
 
-    def __call__(self, batch, check: bool = True):
+    def __call__(self, batch, check: bool = True, slot: int = 0):
         """Same contract as ``model(batch)``: returns the dict of predictions (tensors owned by the graph: valid until
-        the next call with the same shape)."""
-        sig = self._signature(batch)
+        the next call with the same shape and slot).  ``slot`` selects one of several independent captures of the same
+        shape (double buffering: the inputs of step i+1 are copied in while step i runs)."""
+        sig = self._signature(batch, slot)
         ent = self._graphs.get(sig)
         if ent is None:
             ent = self._capture(batch)
@@ -63,10 +64,14 @@ class CapturedForward:
             ops.raise_on_flag(flag)
         return out
 
-    def static_inputs(self, batch):
+    def static_inputs(self, batch, slot: int = 0):
         """The graph's input buffers for this batch shape (capture on first use); writing into them directly (e.g. a
         pinned-host -> device copy) saves the extra device-to-device copy of ``__call__``."""
-        sig = self._signature(batch)
+        sig = self._signature(batch, slot)
         if sig not in self._graphs:
             self._graphs[sig] = self._capture(batch)
         return self._graphs[sig][1]
+
+    def error_flag(self, batch, slot: int = 0):
+        """Device error word of the capture for this batch shape / slot (read it after the replay has finished)."""
+        return self._graphs[self._signature(batch, slot)][3]
