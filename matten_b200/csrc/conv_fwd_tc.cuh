@@ -47,10 +47,19 @@ constexpr int kTcMaxNodes = 16;       // receiver nodes per chunk
 constexpr int kTcD = 5;               // 2*lmax+1 of the types this kernel handles (l <= 2)
 
 // debugging aid: per-warp progress codes of CTA `dbg_block` into a host-visible buffer (MT_CONV_TC_DEBUG)
-#define MT_DBG(code) do { if (p.dbg && (threadIdx.x & 31) == 0) ((volatile long long*)p.dbg)[256 + blockIdx.x * 32 + (threadIdx.x >> 5)] = (long long)(code); } while (0)
 // phase timing of CTA 0 (MT_CONV_TC_DEBUG = device pointer to >= 16384 int64): slot layout in tools/tc_debug.py
+// (compiled in only with -DMT_TC_TIMING: the extra code in the consumer loop costs instruction-cache hits)
+#ifdef MT_TC_TIMING
 #define MT_TACC(var) do { if (p.dbg && blockIdx.x == 0) { const long long _n = clock64(); (var) += _n - _tl; _tl = _n; } } while (0)
+#define MT_TIMING_ONLY(...) __VA_ARGS__
+#define MT_DBG(code) do { if (p.dbg && (threadIdx.x & 31) == 0) ((volatile long long*)p.dbg)[256 + blockIdx.x * 32 + (threadIdx.x >> 5)] = (long long)(code); } while (0)
 #define MT_DBG_BLOCK(code) do { if (p.dbg && threadIdx.x == 0) ((volatile long long*)p.dbg)[blockIdx.x] = (long long)(code); } while (0)
+#else
+#define MT_TACC(var) do { } while (0)
+#define MT_TIMING_ONLY(...)
+#define MT_DBG(code) do { } while (0)
+#define MT_DBG_BLOCK(code) do { } while (0)
+#endif
 
 struct ConvTcParams {
   int x_dim, y_dim, out_dim;
@@ -522,7 +531,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
     }
     int e_carry = -1;  // >= 0: the next chunk continues node n_cur at this global edge
     int b_uses = 0;    // chunks that loaded the h planes so far
-    long long _tl = clock64(), t_we = 0, t_meta = 0, t_wb = 0, t_pad = 0, t_issue = 0, n_chunks = 0;
+    MT_TIMING_ONLY(long long _tl = clock64(), t_we = 0, t_meta = 0, t_wb = 0, t_pad = 0, t_issue = 0;)
+    long long n_chunks = 0;
     const uint32_t xrow_bytes = (uint32_t)p.x_dim * 4, yrow_bytes = (uint32_t)p.y_pad * 4;
     for (int k = 0;; ++k) {
       const int b = k & 1;
@@ -683,16 +693,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
         n_cur += m;
       }
     }
-    if (p.dbg && blockIdx.x == 0 && lane == 0) {
+    MT_TIMING_ONLY(if (p.dbg && blockIdx.x == 0 && lane == 0) {
       p.dbg[8192 + 0] = t_we; p.dbg[8192 + 1] = t_meta; p.dbg[8192 + 2] = t_wb; p.dbg[8192 + 3] = t_pad;
       p.dbg[8192 + 4] = t_issue; p.dbg[8192 + 6] = n_chunks;
-    }
+    })
+    (void)n_chunks;
   } else if (warp == 2 || warp == 3) {
     // ================================================================ gathered x rows: one bulk copy per edge
     // (a UBLKCP is issued lane by lane, ~100 cycles each: two warps on two schedulers halve the issue time)
     const int part = warp - 2;
     const uint32_t xrow_bytes = (uint32_t)p.x_dim * 4;
-    long long _tl = clock64(), t_wg = 0, t_cp = 0;
+    MT_TIMING_ONLY(long long _tl = clock64(), t_wg = 0, t_cp = 0;)
     for (int k = 0;; ++k) {
       const int b = k & 1;
       const TcMeta& M = b ? *meta1 : *meta0;
@@ -711,14 +722,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
       }
       MT_TACC(t_cp);
     }
-    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 10 + 2 * part] = t_wg; p.dbg[8192 + 11 + 2 * part] = t_cp; }
+    MT_TIMING_ONLY(if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 10 + 2 * part] = t_wg; p.dbg[8192 + 11 + 2 * part] = t_cp; })
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     const uint32_t idesc = make_idesc_bf16(128, NE);
     const uint32_t a_lbo = (uint32_t)MT * 128 * 16, b_lbo = (uint32_t)NE * 16;
     const uint64_t a_desc0 = make_kmajor_desc(smem_u32(sA), a_lbo, 128);
     const uint64_t b_desc0 = make_kmajor_desc(smem_u32(sB), b_lbo, 128);
-    long long _tl = clock64(), t_wr = 0, t_mma = 0;
+    MT_TIMING_ONLY(long long _tl = clock64(), t_wr = 0, t_mma = 0;)
     for (int k = 0;; ++k) {  // k counts the chunks that carry edges (and the terminator)
       MT_DBG(2000 + k * 10 + 0);
       // lane 0 alone reads the hand-over word: by the time the other lanes get here the producer may already
@@ -759,13 +770,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
       MT_TACC(t_mma);
       MT_DBG(2000 + k * 10 + 2);
     }
-    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 8] = t_wr; p.dbg[8192 + 9] = t_mma; }
+    MT_TIMING_ONLY(if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 8] = t_wr; p.dbg[8192 + 9] = t_mma; })
   } else if (warp >= kTcProducerWarps) {
     // ================================================================ consumers
     const int q = warp & 3;
     const int nsubq = p.q_count[q];
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
-    long long _tl = clock64(), t_wf = 0, t_work = 0;
+    MT_TIMING_ONLY(long long _tl = clock64(), t_wf = 0, t_work = 0;)
     for (int k = 0;; ++k) {
       const int b = k & 1;
       MT_DBG(3000 + k * 100 + 0);
@@ -792,7 +803,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
         const int d3 = hd >> 28;
         const TcSlot slot = sSlot[sub * 32 + lane];
         const int cb = M.cb[nj], ngrp = M.ngrp[nj];
-        const long long u0 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;
+        MT_TIMING_ONLY(const long long u0 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;)
         float acc[kTcD];
 #pragma unroll
         for (int m = 0; m < kTcD; ++m) acc[m] = 0.f;
@@ -816,10 +827,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
 #pragma unroll
           for (int m = 0; m < kTcD; ++m) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], off);
         }
-        if (p.dbg && blockIdx.x == 0 && lane == 0) {
+        MT_TIMING_ONLY(if (p.dbg && blockIdx.x == 0 && lane == 0) {
           atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg) + 8192 + 128 + sub, (unsigned long long)(clock64() - u0));
           atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg) + 8192 + 256 + sub, 1ull);
-        }
+        })
         if (slot.valid && lane < cpw) {
           float* o = p.out + (size_t)M.node_id[nj] * p.out_dim + slot.ooff;
           const float den = M.den[nj];
@@ -841,7 +852,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTc
       if (lane == 0) mbar_arrive(&bar_empty[b]);
       MT_TACC(t_work);
     }
-    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 16 + 2 * warp] = t_wf; p.dbg[8192 + 17 + 2 * warp] = t_work; }
+    MT_TIMING_ONLY(if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 16 + 2 * warp] = t_wf; p.dbg[8192 + 17 + 2 * warp] = t_work; })
   }
   // ---------------------------------------------------------------- teardown
   MT_DBG(9000);

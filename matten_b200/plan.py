@@ -176,8 +176,16 @@ class UVUPlan:
         hdr = [[0] * 8 for _ in subs]
         slot = [[[0, 0, 0, 0] for _ in range(32)] for _ in subs]
         qlist = [[] for _ in range(4)]
+        # quarters <-> warp schedulers: the 7 consumer warps of quarter q share scheduler q and its instruction
+        # cache, so besides balancing the cost, keep the number of DISTINCT contraction types per quarter small
+        # (ncu r1: instruction fetch was the top stall of the 64-column kernels)
+        type_penalty = float(os.environ.get("MT_TC_TYPE_PENALTY", "2.0"))
+        qtypes = [set() for _ in range(4)]
         for g in groups:
-            q = min((q for q in range(4) if qn[q] < MT), key=lambda q: qcost[q])
+            gt = {(subs[i]["type"], subs[i]["cpw"] == 32) for i, _ in g["subs"]}  # (type, loop variant) = code
+            q = min((q for q in range(4) if qn[q] < MT),
+                    key=lambda q: qcost[q] + type_penalty * len(gt - qtypes[q]))
+            qtypes[q] |= gt
             t = qn[q]
             qn[q] += 1
             qcost[q] += g["cost"]
