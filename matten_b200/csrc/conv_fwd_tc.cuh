@@ -290,9 +290,17 @@ __global__ void __launch_bounds__(kPrepThreads) edge_prepare_kernel(const ConvTc
     const int64_t orig = p.perm[e];
     // sh row, padded
     {
-      const float* yr = p.sh + orig * p.y_dim;
-      float* yo = p.ysorted + e * p.y_pad;
-      for (int j = 0; j < p.y_pad; ++j) yo[j] = (j < p.y_dim) ? yr[j] : 0.f;
+      // loads first, stores after: a store waiting for its load would block the next load behind it (in-order issue)
+      const float* __restrict__ yr = p.sh + orig * p.y_dim;
+      float* __restrict__ yo = p.ysorted + e * p.y_pad;
+      for (int j0 = 0; j0 < p.y_pad; j0 += 12) {
+        float yv[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) yv[j] = (j0 + j < p.y_dim) ? yr[j0 + j] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 12; j += 4)
+          if (j0 + j < p.y_pad) *reinterpret_cast<float4*>(yo + j0 + j) = make_float4(yv[j], yv[j + 1], yv[j + 2], yv[j + 3]);
+      }
     }
     float h[kTcK];
 #pragma unroll
@@ -311,7 +319,7 @@ __global__ void __launch_bounds__(kPrepThreads) edge_prepare_kernel(const ConvTc
 #pragma unroll
       for (int j = 0; j < kTcK; ++j) a[j] = 0.f;
       const float* W = sW[li];
-#pragma unroll 1
+#pragma unroll 4
       for (int k = 0; k < fi; ++k) {
         const float hk = hrow[k];
         const float4* wr = reinterpret_cast<const float4*>(W + k * kTcK);
