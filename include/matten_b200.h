@@ -130,6 +130,25 @@ int mt_gather_i64_to_i32(const int64_t* src, const int32_t* perm, int64_t n, int
 /* Sets MT_FLAG_UNSORTED if keys is not non-decreasing. */
 int mt_check_sorted(const int64_t* keys, int64_t n, int32_t* err_flag, mt_stream stream);
 
+/* a16: periodic neighbour list of a batch of crystals on the GPU.  Replaces
+ * neighbor_list_and_relative_vec (reference src/matten/data/data.py:285-413: ASE primitive_neighbor_list("ijS",
+ * self_interaction=True) minus the true self edges).  Every ordered pair (i, j, S) of one crystal with
+ * |pos[j] - pos[i] + S @ cell| < r_max except (i == j, S == 0); all arithmetic in fp64 whatever `dtype` is; edges in
+ * the canonical order (i, j, Sx, Sy, Sz).  Two calls, because the edge count is data dependent:
+ *   mt_neighbor_count: offsets [N+1] = exclusive scan of the per-centre neighbour counts, offsets[N] = E
+ *                      (the caller reads offsets[N] to size the outputs: the one synchronisation of graph building);
+ *   mt_neighbor_fill : edge_index [2,E] int64 (row 0 = centre i, row 1 = neighbour j), edge_cell_shift [E,3] and
+ *                      num_neigh [N] (may be NULL) in `dtype` (the reference stores both as floats).
+ * pos [N,3], cell [B,3,3] in `dtype`; batch [N] int64 (NULL when B == 1); ptr [B+1] int64 node offsets of the graphs.
+ * workspace: mt_neighbor_workspace_bytes(N, B), shared by the two calls. */
+size_t mt_neighbor_workspace_bytes(int64_t N, int64_t B);
+int mt_neighbor_count(int dtype, const void* pos, const void* cell, const int64_t* batch, const int64_t* ptr,
+                      int64_t N, int64_t B, double r_max, int32_t* offsets, void* workspace, size_t workspace_bytes,
+                      mt_stream stream);
+int mt_neighbor_fill(int dtype, const void* pos, const int64_t* batch, const int64_t* ptr, int64_t N, int64_t B,
+                     double r_max, const int32_t* offsets, const void* workspace, int64_t* edge_index,
+                     void* edge_cell_shift, void* num_neigh, int64_t E, mt_stream stream);
+
 /* a4: _AtomicNumberToIndex + one-hot + Linear(S, dim, bias), reference
  * src/matten/nn/embedding.py:85-110, 206-263.
  *   idx = lut[Z - min_Z] (MT_FLAG_BAD_SPECIES if Z out of range or lut == -1)

@@ -354,6 +354,106 @@ __global__ void __launch_bounds__(256) species_embed_kernel(
     for (int j = lane; j < dim; j += 32) feats[n * dim + j] = lin_w[(int64_t)j * S + s] + lin_b[j];
 }
 
+
+// =========================================================================
+// periodic neighbour list (reference src/matten/data/data.py:285-413: ASE primitive_neighbor_list("ijS") with
+// self_interaction=True, then the true self edges (i == j, S == 0) dropped).  All arithmetic in fp64, like the
+// reference's numpy/ASE path.  Edges of centre i are emitted in the canonical order (j, Sx, Sy, Sz), centres in
+// ascending order: the same order as matten_b200/data/neighbors.py.
+// =========================================================================
+struct NlGraph {
+  double c[9];   // cell rows
+  int R[3];      // images per axis: ceil(r_max / height) + span of the fractional coordinates
+  int pad;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) nl_setup_kernel(const T* __restrict__ pos, const T* __restrict__ cell,
+                                                       const int64_t* __restrict__ ptr, int64_t B, double r_max,
+                                                       NlGraph* __restrict__ out) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  NlGraph g;
+  for (int k = 0; k < 9; ++k) g.c[k] = (double)cell[b * 9 + k];
+  const double* c = g.c;
+  const double det = c[0] * (c[4] * c[8] - c[5] * c[7]) - c[1] * (c[3] * c[8] - c[5] * c[6]) +
+                     c[2] * (c[3] * c[7] - c[4] * c[6]);
+  const double vol = fabs(det);
+  int span = 0;
+  if (vol > 0) {
+    // inverse (adjugate / det): frac = pos @ inv(cell)
+    double inv[9];
+    inv[0] = (c[4] * c[8] - c[5] * c[7]) / det; inv[1] = (c[2] * c[7] - c[1] * c[8]) / det; inv[2] = (c[1] * c[5] - c[2] * c[4]) / det;
+    inv[3] = (c[5] * c[6] - c[3] * c[8]) / det; inv[4] = (c[0] * c[8] - c[2] * c[6]) / det; inv[5] = (c[2] * c[3] - c[0] * c[5]) / det;
+    inv[6] = (c[3] * c[7] - c[4] * c[6]) / det; inv[7] = (c[1] * c[6] - c[0] * c[7]) / det; inv[8] = (c[0] * c[4] - c[1] * c[3]) / det;
+    double fmin = 1e300, fmax = -1e300;
+    for (int64_t i = ptr[b]; i < ptr[b + 1]; ++i) {
+      const double x = (double)pos[i * 3], y = (double)pos[i * 3 + 1], z = (double)pos[i * 3 + 2];
+      for (int k = 0; k < 3; ++k) {
+        const double f = x * inv[k] + y * inv[3 + k] + z * inv[6 + k];
+        fmin = f < fmin ? f : fmin;
+        fmax = f > fmax ? f : fmax;
+      }
+    }
+    if (ptr[b + 1] > ptr[b]) span = (int)ceil(fmax - fmin);
+  }
+  for (int k = 0; k < 3; ++k) {
+    int r = 0;
+    if (vol > 0) {
+      const double* a = c + 3 * ((k + 1) % 3);
+      const double* d = c + 3 * ((k + 2) % 3);
+      const double cx = a[1] * d[2] - a[2] * d[1], cy = a[2] * d[0] - a[0] * d[2], cz = a[0] * d[1] - a[1] * d[0];
+      const double height = vol / sqrt(cx * cx + cy * cy + cz * cz);
+      r = (int)ceil(r_max / height) + span;
+    }
+    g.R[k] = r;
+  }
+  g.pad = 0;
+  out[b] = g;
+}
+
+// FILL == false: counts[i] = number of neighbours of centre i; FILL == true: write them at offsets[i]
+template <typename T, bool FILL>
+__global__ void __launch_bounds__(128) nl_pairs_kernel(const T* __restrict__ pos, const int64_t* __restrict__ batch,
+                                                       const int64_t* __restrict__ ptr,
+                                                       const NlGraph* __restrict__ graphs, int64_t N, double r2,
+                                                       int32_t* __restrict__ counts,
+                                                       const int32_t* __restrict__ offsets,
+                                                       int64_t* __restrict__ ei, int64_t E, T* __restrict__ shifts,
+                                                       T* __restrict__ num_neigh) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int64_t b = batch ? batch[i] : 0;
+  const NlGraph g = graphs[b];
+  const double xi = (double)pos[i * 3], yi = (double)pos[i * 3 + 1], zi = (double)pos[i * 3 + 2];
+  int64_t w = FILL ? offsets[i] : 0;
+  int cnt = 0;
+  for (int64_t j = ptr[b]; j < ptr[b + 1]; ++j) {
+    const double dx0 = (double)pos[j * 3] - xi, dy0 = (double)pos[j * 3 + 1] - yi, dz0 = (double)pos[j * 3 + 2] - zi;
+    for (int sx = -g.R[0]; sx <= g.R[0]; ++sx)
+      for (int sy = -g.R[1]; sy <= g.R[1]; ++sy)
+        for (int sz = -g.R[2]; sz <= g.R[2]; ++sz) {
+          // offset = S @ cell, then d = (pos[j] - pos[i]) + offset, |d|^2 = (dx^2 + dy^2) + dz^2 without contraction
+          const double ox = fma((double)sz, g.c[6], fma((double)sy, g.c[3], (double)sx * g.c[0]));
+          const double oy = fma((double)sz, g.c[7], fma((double)sy, g.c[4], (double)sx * g.c[1]));
+          const double oz = fma((double)sz, g.c[8], fma((double)sy, g.c[5], (double)sx * g.c[2]));
+          const double dx = dx0 + ox, dy = dy0 + oy, dz = dz0 + oz;
+          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+          if (d2 < r2 && !(j == i && sx == 0 && sy == 0 && sz == 0)) {
+            if (FILL) {
+              ei[w] = i;
+              ei[E + w] = j;
+              shifts[w * 3] = (T)sx; shifts[w * 3 + 1] = (T)sy; shifts[w * 3 + 2] = (T)sz;
+              ++w;
+            }
+            ++cnt;
+          }
+        }
+  }
+  if (FILL) { if (num_neigh) num_neigh[i] = (T)cnt; }
+  else counts[i] = cnt;
+}
+
 }  // namespace mt
 
 // ===========================================================================
@@ -526,6 +626,56 @@ int mt_species_embed(int dtype, const int64_t* atomic_numbers, int z_given, cons
     species_embed_kernel<T><<<grid_for(N * 32, 256), 256, 0, as_stream(stream)>>>(
         atomic_numbers, z_given, lut, min_z, max_z, num_species, dim, (const T*)lin_w, (const T*)lin_b, N,
         species_index, (T*)node_attrs, (T*)node_feats, err_flag);
+  });
+  MT_LAUNCH_OK();
+  return MT_OK;
+}
+
+
+size_t mt_neighbor_workspace_bytes(int64_t N, int64_t B) {
+  return ((size_t)(B > 0 ? B : 1) * sizeof(NlGraph) + 255) / 256 * 256 + (scan_tmp_elems(N + 1) + 8) * sizeof(int32_t);
+}
+
+int mt_neighbor_count(int dtype, const void* pos, const void* cell, const int64_t* batch, const int64_t* ptr,
+                      int64_t N, int64_t B, double r_max, int32_t* offsets, void* workspace, size_t workspace_bytes,
+                      mt_stream stream) {
+  MT_ENTRY_GUARD();
+  MT_REQUIRE(N >= 0 && B >= 1 && r_max > 0, "bad arguments");
+  MT_REQUIRE(pos && cell && ptr && offsets && workspace, "null pointer");
+  MT_REQUIRE(B == 1 || batch != nullptr, "batch vector required for more than one graph");
+  MT_REQUIRE(workspace_bytes >= mt_neighbor_workspace_bytes(N, B), "neighbour-list workspace too small");
+  cudaStream_t st = as_stream(stream);
+  NlGraph* graphs = static_cast<NlGraph*>(workspace);
+  int32_t* tmp = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(workspace) +
+                                            ((size_t)B * sizeof(NlGraph) + 255) / 256 * 256);
+  MT_DISPATCH_DTYPE(dtype, {
+    nl_setup_kernel<T><<<grid_for(B, 128), 128, 0, st>>>((const T*)pos, (const T*)cell, ptr, B, r_max, graphs);
+  });
+  MT_LAUNCH_OK();
+  MT_CUDA_OK(cudaMemsetAsync(offsets + N, 0, sizeof(int32_t), st));
+  if (N > 0) {
+    MT_DISPATCH_DTYPE(dtype, {
+      nl_pairs_kernel<T, false><<<grid_for(N, 128), 128, 0, st>>>((const T*)pos, batch, ptr, graphs, N, r_max * r_max,
+                                                                   offsets, nullptr, nullptr, 0, nullptr, nullptr);
+    });
+    MT_LAUNCH_OK();
+  }
+  return exclusive_scan_i32(offsets, N + 1, tmp, st);  // offsets[N] = number of edges
+}
+
+int mt_neighbor_fill(int dtype, const void* pos, const int64_t* batch, const int64_t* ptr, int64_t N, int64_t B,
+                     double r_max, const int32_t* offsets, const void* workspace, int64_t* edge_index,
+                     void* edge_cell_shift, void* num_neigh, int64_t E, mt_stream stream) {
+  MT_ENTRY_GUARD();
+  MT_REQUIRE(N >= 0 && B >= 1 && E >= 0, "bad arguments");
+  if (N == 0) return MT_OK;
+  MT_REQUIRE(pos && ptr && offsets && workspace, "null pointer");
+  MT_REQUIRE(E == 0 || (edge_index && edge_cell_shift), "null output pointer");
+  const NlGraph* graphs = static_cast<const NlGraph*>(workspace);
+  MT_DISPATCH_DTYPE(dtype, {
+    nl_pairs_kernel<T, true><<<grid_for(N, 128), 128, 0, as_stream(stream)>>>(
+        (const T*)pos, batch, ptr, graphs, N, r_max * r_max, nullptr, offsets, edge_index, E, (T*)edge_cell_shift,
+        (T*)num_neigh);
   });
   MT_LAUNCH_OK();
   return MT_OK;

@@ -114,3 +114,30 @@ def collate(graphs: Sequence[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor
 def to_device(batch: Dict[str, torch.Tensor], device, non_blocking: bool = True) -> Dict[str, torch.Tensor]:
     return {k: (v.to(device, non_blocking=non_blocking) if isinstance(v, torch.Tensor) else v)
             for k, v in batch.items()}
+
+
+def batch_from_structures(structs: Sequence[dict], r_cut: float, device, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Batched graph dict built ON THE GPU: positions / cells / atomic numbers of all crystals are uploaded once and the
+    periodic neighbour list of the whole batch comes from ``ops.neighbor_list`` (one kernel pair instead of one
+    host-side numpy search per crystal).  ``structs``: dicts with ``cart`` [n,3], ``lattice`` [3,3], ``Z`` [n]
+    (``matten_b200.predict._structure_arrays``).  Same keys, dtypes and edge order as ``collate(make_graph(...))``."""
+    from .. import ops
+
+    n_nodes = [len(s["Z"]) for s in structs]
+    offs = np.concatenate([[0], np.cumsum(n_nodes)])
+    pos = torch.as_tensor(np.concatenate([np.asarray(s["cart"], dtype=np.float64).reshape(-1, 3) for s in structs]))
+    cell = torch.as_tensor(np.stack([np.asarray(s["lattice"], dtype=np.float64).reshape(3, 3) for s in structs]))
+    out = {
+        "pos": pos.to(device=device, dtype=dtype),
+        "cell": cell.to(device=device, dtype=dtype).reshape(-1, 3),
+        "atomic_numbers": torch.as_tensor(np.concatenate([np.asarray(s["Z"], dtype=np.int64) for s in structs])).to(device),
+        "batch": torch.repeat_interleave(torch.arange(len(structs)), torch.as_tensor(n_nodes)).to(device),
+        "ptr": torch.as_tensor(offs, dtype=torch.int64).to(device),
+        "num_graphs": len(structs),
+    }
+    # the search itself runs in fp64 from the fp64 inputs (like the reference's numpy/ASE path), whatever `dtype` is
+    ei, sh, nn = ops.neighbor_list(pos.to(device), cell.to(device), out["batch"], out["ptr"], r_cut)
+    out["edge_index"] = ei
+    out["edge_cell_shift"] = sh.to(dtype)
+    out["num_neigh"] = nn.to(dtype)
+    return out

@@ -118,6 +118,31 @@ def edge_radial(edge_len, mode: int, num_basis: int, start: float, end: float, c
     return out
 
 
+def neighbor_list(pos, cell, batch, ptr, r_max: float):
+    """Periodic neighbour list of a batch of crystals on the GPU (reference data/data.py:285-413 semantics).
+    pos [N,3], cell [B,3,3] (same float dtype), batch [N] int64, ptr [B+1] int64.
+    Returns (edge_index [2,E] int64, edge_cell_shift [E,3], num_neigh [N]) in the canonical (i, j, S) order."""
+    lib = _lib.load()
+    pos = _req(pos, "pos")
+    cell = _req(cell, "cell", pos.dtype).reshape(-1, 3, 3)
+    ptr = _req(ptr, "ptr", torch.int64)
+    N, B = pos.shape[0], cell.shape[0]
+    if B > 1:
+        batch = _req(batch, "batch", torch.int64)
+    offsets = torch.empty(N + 1, dtype=torch.int32, device=pos.device)
+    nbytes = lib.mt_neighbor_workspace_bytes(N, B)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=pos.device)
+    check(lib.mt_neighbor_count(_dt(pos), _p(pos), _p(cell), _p(batch) if B > 1 else None, _p(ptr), N, B, float(r_max),
+                                _p(offsets), _p(ws), nbytes, _stream(pos)))
+    E = int(offsets[-1].item())  # the one synchronisation of graph building: the edge count sizes the outputs
+    ei = torch.empty((2, E), dtype=torch.int64, device=pos.device)
+    shifts = torch.empty((E, 3), dtype=pos.dtype, device=pos.device)
+    num_neigh = torch.empty(N, dtype=pos.dtype, device=pos.device)
+    check(lib.mt_neighbor_fill(_dt(pos), _p(pos), _p(batch) if B > 1 else None, _p(ptr), N, B, float(r_max),
+                               _p(offsets), _p(ws), _p(ei), _p(shifts), _p(num_neigh), E, _stream(pos)))
+    return ei, shifts, num_neigh
+
+
 # ------------------------------------------------------------ bookkeeping --
 def csr_by_key(keys, num_keys: int, want_perm: bool = True, flag=None):
     """Stable sort of int64 keys -> (rowptr int32 [num_keys+1], perm int32 [E] | None)."""

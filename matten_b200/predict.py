@@ -24,7 +24,6 @@ from typing import Any, Dict, List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from .data.neighbors import collate, make_graph, to_device
 from .model_factory.tfn_atomic_tensor import AtomicTensorModel
 from .model_factory.tfn_scalar_tensor import ScalarTensorModel
 from .nn.readout import CartesianTensorWrapper
@@ -155,26 +154,48 @@ def get_pretrained_model(identifier: str, checkpoint: str = "model_final.ckpt", 
 
 
 # ------------------------------------------------------------------------------------------ evaluation
-def _graphs(structs: Sequence[Dict[str, Any]], r_cut: float, dtype):
-    graphs, failed = [], []
-    for i, s in enumerate(structs):
-        try:  # reference dataset/structure_scalar_tensor.py:357-362: failed conversions are skipped
-            graphs.append(make_graph(s["cart"], s["lattice"], s["Z"], r_cut, dtype=dtype))
-        except Exception as e:  # noqa: BLE001
-            warnings.warn(f"Failed converting structure {i}: {e}. Skip it.")
-            failed.append(i)
-    return graphs, failed
+def _edge_counts(batch) -> List[int]:
+    """edges per crystal of a GPU-built batch (num_neigh summed per graph; tiny)."""
+    from . import ops
+
+    ptr32 = batch["ptr"].to(torch.int32)
+    return [int(v) for v in ops.segment_reduce(batch["num_neigh"].reshape(-1, 1).contiguous(), ptr32, "sum").reshape(-1).cpu()]
 
 
-def evaluate(model, graphs: List[Dict[str, torch.Tensor]], batch_size: int, device, tensor_target_name: str,
-             tensor_target_formula: str = "ijkl=jikl=klij") -> List[torch.Tensor]:
-    """reference src/matten/predict.py:117-148: batches of ``batch_size`` graphs, irreps -> Cartesian."""
+def _build_batches(structs: Sequence[Dict[str, Any]], idx: Sequence[int], batch_size: int, r_cut: float, device, dtype):
+    """Batched graphs of the structures ``idx`` built on the GPU (``data.neighbors.batch_from_structures``), in chunks
+    of ``batch_size``.  A crystal without any edge inside ``r_cut`` cannot be converted (the reference raises "After
+    eliminating self edges, no edges remain" and skips it, dataset/structure_scalar_tensor.py:357-362): it is reported
+    in ``failed`` and left out.  Yields (batch, kept indices, edge counts)."""
+    from .data.neighbors import batch_from_structures
+
+    out, failed = [], []
+    for i in range(0, len(idx), batch_size):
+        chunk = list(idx[i:i + batch_size])
+        batch = batch_from_structures([structs[j] for j in chunk], r_cut, device, dtype)
+        counts = _edge_counts(batch)
+        bad = [j for j, c in zip(chunk, counts) if c == 0]
+        if bad:
+            for j in bad:
+                warnings.warn(f"Failed converting structure {j}: After eliminating self edges, no edges remain in "
+                              f"this system. Skip it.")
+            failed += bad
+            chunk = [j for j in chunk if j not in set(bad)]
+            if not chunk:
+                continue
+            batch = batch_from_structures([structs[j] for j in chunk], r_cut, device, dtype)
+            counts = [c for c in counts if c > 0]
+        out.append((batch, chunk, counts))
+    return out, failed
+
+
+def evaluate(model, batches, tensor_target_name: str, tensor_target_formula: str = "ijkl=jikl=klij") -> List[torch.Tensor]:
+    """reference src/matten/predict.py:117-148: one forward per batch, irreps -> Cartesian."""
     converter = CartesianTensorWrapper(tensor_target_formula)
     out: List[torch.Tensor] = []
     model.eval()
     with torch.no_grad():
-        for i in range(0, len(graphs), batch_size):
-            batch = to_device(collate(graphs[i:i + batch_size]), device)
+        for batch in batches:
             p = model(batch)[tensor_target_name]
             out.extend(converter.to_cartesian(p).cpu())
     return out
@@ -200,22 +221,29 @@ def predict(structure, model_identifier="20230627", checkpoint: str = "model_fin
     config = get_pretrained_config(model_identifier)
     name = config["data"]["tensor_target_name"]
     formula = config["data"]["tensor_target_formula"]
+    r_cut = float(config["data"]["r_cut"])
     model.task_name = name
     dtype = next(model.parameters()).dtype
-    graphs, failed = _graphs(structs, float(config["data"]["r_cut"]), dtype)
+    rank_dims = (3,) * len(formula.split("=")[0])
 
     dist = torch.distributed
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    built, failed = _build_batches(structs, list(range(len(structs))), batch_size, r_cut, device, dtype)
     if world > 1 and not is_atomic_tensor:
-        shards = shard_by_edges([int(g["edge_index"].shape[1]) for g in graphs], world)
-        mine = shards[dist.get_rank()]
-        local = evaluate(model, [graphs[i] for i in mine], batch_size, device, name, formula)
-        flat = (torch.stack(local).reshape(len(local), -1) if local else
-                torch.zeros((0, 3 ** len(formula.split("=")[0])), dtype=dtype)).to(device)
+        # shard the convertible crystals over the ranks by edge count; every rank ends up with the full result list
+        kept = [j for _, chunk, _ in built for j in chunk]
+        counts = [c for _, _, cs in built for c in cs]
+        shards = shard_by_edges(counts, world)
+        mine = [kept[i] for i in shards[dist.get_rank()]]
+        del built
+        mine_built, _ = _build_batches(structs, mine, batch_size, r_cut, device, dtype)
+        local = evaluate(model, [b for b, _, _ in mine_built], name, formula)
+        width = int(np.prod(rank_dims))
+        flat = (torch.stack(local).reshape(len(local), -1) if local else torch.zeros((0, width), dtype=dtype)).to(device)
         allp = gather_predictions(flat, [len(s) for s in shards]).cpu()
-        predictions = list(allp.reshape((allp.shape[0],) + (3,) * len(formula.split("=")[0])))
+        predictions = list(allp.reshape((allp.shape[0],) + rank_dims))
     else:
-        predictions = evaluate(model, graphs, batch_size, device, name, formula)
+        predictions = evaluate(model, [b for b, _, _ in built], name, formula)
 
     if is_elasticity_tensor:
         try:
