@@ -48,6 +48,16 @@ def main():
     print("n100:", len(structs), "crystals,", sum(len(s["atomic_numbers"]) for s in structs), "atoms,",
           len({z for s in structs for z in s["atomic_numbers"]}), "elements")
 
+    # small slices of the two example datasets IN THE REFERENCE'S OWN FILE FORMAT (pandas-style column JSON with
+    # pymatgen Structure dicts): inputs of the dataset-reader / training tests
+    keep = keys[:6]
+    json.dump({c: {k: d[c][k] for k in keep} for c in ("structure", "elastic_tensor_full")},
+              open(os.path.join(HERE, "elasticity_n6_reference_format.json"), "w"))
+    n = json.load(open(os.path.join(REF, "datasets/si_nmr_data.json")))
+    nk = [k for k in sorted(n["structure"].keys(), key=int) if len(n["species"][k]) <= 30][:4]
+    json.dump({c: {k: n[c][k] for k in nk} for c in ("structure", "nmr_tensor", "atom_selector")},
+              open(os.path.join(HERE, "si_nmr_n4_reference_format.json"), "w"))
+
     from matten_b200.data.synthetic import synthetic_batch
     from oracle import matten_restated as M
     from tests.helpers import HP_LMAX2, SPECIES8, randomize_bn
