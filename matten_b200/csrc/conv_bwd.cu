@@ -124,6 +124,10 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
   {
     const double avg_deg = N > 0 ? (double)E / (double)N : 1.0;
     const size_t fixed = (size_t)p.num_paths * 16;
+    // resident CTAs per SM the register budget allows (launch bounds of conv_bwd_kernel) -> shared-memory budget per CTA:
+    // the kernel alternates staging / GEMM / contraction phases between barriers, so more small CTAs hide more of it
+    const int per_sm_regs = sizeof(T) == 4 ? 3 : 2;
+    const size_t budget = (size_t)(227 * 1024) / per_sm_regs - 1024;
     int EC = 32, TN = 1;
     size_t smem = 0;
     for (;;) {
@@ -133,10 +137,10 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
       for (;;) {
         smem = fixed + ((size_t)EC * (p.hs_stride + p.xs_stride + p.y_dim + p.wt_stride) + (size_t)TN * (p.out_dim + 1)) * sizeof(T) +
                (size_t)EC * sizeof(int);
-        if (smem <= 110 * 1024 || TN == 1) break;
+        if (smem <= budget || TN == 1) break;
         TN = TN / 2;
       }
-      if (smem <= 110 * 1024 || EC == 8) break;
+      if (smem <= budget || EC == 8) break;
       EC /= 2;
     }
     MT_REQUIRE(smem <= 227 * 1024, "conv_bwd tile needs %zu bytes of shared memory", smem);
@@ -148,7 +152,9 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
       cfg1 = smem;
     }
     const int64_t tiles = ceil_div<int64_t>(N, TN);
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    if (per_sm > per_sm_regs) per_sm = per_sm_regs;
+    if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)kNumSMs * per_sm;
     if (grid > tiles) grid = tiles;
     conv_bwd_kernel<T><<<(int)grid, 256, smem, st>>>(p);

@@ -177,7 +177,7 @@ __device__ __forceinline__ void bwd_unit(const ConvBwdParams& p, const int4* __r
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 2) conv_bwd_kernel(const ConvBwdParams p) {
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 2) conv_bwd_kernel(const ConvBwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int EC = p.chunk_edges;
   int4* spath = reinterpret_cast<int4*>(smem_raw);     // [num_paths]
