@@ -68,6 +68,30 @@ __host__ __device__ constexpr I ceil_div(I a, I b) {
 
 __host__ __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 
+// ------------------------------------------------------------ packed fp32 --
+// Two fp32 lanes in one register pair: sm_100 issues FFMA2 / FMUL2 (two IEEE fp32 FMAs per instruction).  The
+// generated CG contractions are templates on the scalar type, so instantiating them with f2 processes two edges per
+// instruction stream at half the issue slots -- these kernels are issue-bound, not FMA-pipe-bound.
+struct f2 {
+  float2 v;
+  __device__ __forceinline__ f2() {}
+  __device__ __forceinline__ f2(float a, float b) : v(make_float2(a, b)) {}
+  __device__ __forceinline__ explicit f2(float a) : v(make_float2(a, a)) {}
+  __device__ __forceinline__ explicit f2(double a) : v(make_float2((float)a, (float)a)) {}
+  __device__ __forceinline__ explicit f2(int a) : v(make_float2((float)a, (float)a)) {}
+};
+__device__ __forceinline__ f2 operator*(f2 a, f2 b) {
+  f2 r;
+  r.v = __fmul2_rn(a.v, b.v);
+  return r;
+}
+using ::fma;  // keep the scalar overloads visible next to the packed one
+__device__ __forceinline__ f2 fma(f2 a, f2 b, f2 c) {
+  f2 r;
+  r.v = __ffma2_rn(a.v, b.v, c.v);
+  return r;
+}
+
 // ------------------------------------------------------------ activations --
 template <typename T>
 __device__ __forceinline__ T act_sigmoid(T v) {

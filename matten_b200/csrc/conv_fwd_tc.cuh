@@ -366,21 +366,25 @@ __device__ __forceinline__ void tc_unit(uint32_t taddr, const float* __restrict_
   MT_TMEM_LD_X4(taddr, c0, c1, c2, c3);
   MT_TMEM_LD_WAIT(c0, c1, c2, c3);
   if (cpw == 32) {
-    // lane == TMEM row: every lane walks all columns, two edges per iteration
+    // lane == TMEM row: every lane walks all columns, two edges per iteration packed into FFMA2 / FMUL2 (edge a in
+    // the low half, edge b in the high half of every register pair); the two partial sums are added at the end
+    constexpr int D3 = 2 * L3 + 1;
+    f2 acc2[D3];
+#pragma unroll
+    for (int m = 0; m < D3; ++m) acc2[m] = f2(0.f, 0.f);
 #pragma unroll 1
     for (int g = 0; g < ngrp; ++g) {
       const bool more = g + 1 < ngrp;
       if (more) MT_TMEM_LD_X4(taddr + (uint32_t)(4 * g + 4), n0, n1, n2, n3);  // prefetch the next 4 columns
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
-        const float wa = __uint_as_float(h ? c2 : c0), wb = __uint_as_float(h ? c3 : c1);
-        float xa[D1], ya[D2], xb[D1], yb[D2];
+        const f2 w2(__uint_as_float(h ? c2 : c0), __uint_as_float(h ? c3 : c1));
+        f2 x2[D1], y2[D2];
 #pragma unroll
-        for (int m = 0; m < D1; ++m) { xa[m] = xp[m]; xb[m] = xp[xstride + m]; }
+        for (int m = 0; m < D1; ++m) x2[m] = f2(xp[m], xp[xstride + m]);
 #pragma unroll
-        for (int m = 0; m < D2; ++m) { ya[m] = yp[m]; yb[m] = yp[ystride + m]; }
-        CG<L1, L2, L3>::template fwd<float>(xa, ya, wa, acc);
-        CG<L1, L2, L3>::template fwd<float>(xb, yb, wb, acc);
+        for (int m = 0; m < D2; ++m) y2[m] = f2(yp[m], yp[ystride + m]);
+        CG<L1, L2, L3>::template fwd<f2>(x2, y2, w2, acc2);
         xp += 2 * xstride;
         yp += 2 * ystride;
       }
@@ -389,6 +393,8 @@ __device__ __forceinline__ void tc_unit(uint32_t taddr, const float* __restrict_
         c0 = n0; c1 = n1; c2 = n2; c3 = n3;
       }
     }
+#pragma unroll
+    for (int m = 0; m < D3; ++m) acc[m] += acc2[m].v.x + acc2[m].v.y;
   } else {
     // packed small types: lane = (column j, phase ph); phase ph takes the columns == ph (mod nphase) of every
     // group and fetches its weight from the lane that owns the column's TMEM row
