@@ -92,6 +92,18 @@ __device__ __forceinline__ f2 fma(f2 a, f2 b, f2 c) {
   return r;
 }
 
+// c[0..1] += s * b[0..1] for a register pair (one FFMA2 with a broadcast scalar operand in fp32)
+__device__ __forceinline__ void fma_pair(float s, float b0, float b1, float2& c) {
+  c = __ffma2_rn(make_float2(s, s), make_float2(b0, b1), c);
+}
+__device__ __forceinline__ void fma_pair(double s, double b0, double b1, double2& c) {
+  c.x = fma(s, b0, c.x);
+  c.y = fma(s, b1, c.y);
+}
+template <typename T> struct pair_of;
+template <> struct pair_of<float> { using type = float2; };
+template <> struct pair_of<double> { using type = double2; };
+
 // ------------------------------------------------------------ activations --
 template <typename T>
 __device__ __forceinline__ T act_sigmoid(T v) {

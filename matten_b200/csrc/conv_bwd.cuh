@@ -247,9 +247,10 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 2) conv_bwd_kernel(c
         for (int c = tid; c < Wn; c += 2 * blockDim.x) {
           const int c2 = c + blockDim.x;
           const bool two = c2 < Wn;
-          T acc0[kBwdET], acc1[kBwdET];
+          using P = typename pair_of<T>::type;  // edge pairs: one FFMA2 (broadcast weight) per pair in fp32
+          P acc0[kBwdET / 2], acc1[kBwdET / 2];
 #pragma unroll
-          for (int i = 0; i < kBwdET; ++i) { acc0[i] = T(0); acc1[i] = T(0); }
+          for (int i = 0; i < kBwdET / 2; ++i) { acc0[i].x = acc0[i].y = T(0); acc1[i].x = acc1[i].y = T(0); }
 #pragma unroll 4
           for (int k = 0; k < H; ++k) {
             const T w0 = Wlast[(size_t)k * Wn + c];
@@ -258,16 +259,16 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 2) conv_bwd_kernel(c
             load4<T>(hs + (size_t)k * EC + ep, *reinterpret_cast<T(*)[4]>(&hv[0]));
             load4<T>(hs + (size_t)k * EC + ep + 4, *reinterpret_cast<T(*)[4]>(&hv[4]));
 #pragma unroll
-            for (int i = 0; i < kBwdET; ++i) {
-              acc0[i] = fma(hv[i], w0, acc0[i]);
-              acc1[i] = fma(hv[i], w1, acc1[i]);
+            for (int i = 0; i < kBwdET / 2; ++i) {
+              fma_pair(w0, hv[2 * i], hv[2 * i + 1], acc0[i]);
+              fma_pair(w1, hv[2 * i], hv[2 * i + 1], acc1[i]);
             }
           }
 #pragma unroll
           for (int i = 0; i < kBwdET; ++i)
             if (ep + i < ne) {
-              wt[(size_t)(ep + i) * p.wt_stride + c] = acc0[i];
-              if (two) wt[(size_t)(ep + i) * p.wt_stride + c2] = acc1[i];
+              wt[(size_t)(ep + i) * p.wt_stride + c] = (i & 1) ? acc0[i >> 1].y : acc0[i >> 1].x;
+              if (two) wt[(size_t)(ep + i) * p.wt_stride + c2] = (i & 1) ? acc1[i >> 1].y : acc1[i >> 1].x;
             }
         }
       }
@@ -326,11 +327,12 @@ __global__ void __launch_bounds__(256) mlp_bwd_last_kernel(const ConvBwdParams p
   }
   const int tc = tid & 31, tk = tid >> 5;   // dW tile: columns 4 tc .. 4 tc + 3, k = tk + 8 i
   const int te = tid >> 2, kq = tid & 3;    // dH tile: edge te, k = kq * KD .. + KD - 1
-  T accw[KP][4];
+  using P = typename pair_of<T>::type;  // pairs of columns / of k: one FFMA2 per pair in fp32
+  P accw[KP][2];
 #pragma unroll
   for (int i = 0; i < KP; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) accw[i][j] = T(0);
+    for (int j = 0; j < 2; ++j) accw[i][j].x = accw[i][j].y = T(0);
   const int64_t nchunks = ceil_div<int64_t>(p.E, kLastEB);
   for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const int64_t e0 = ch * kLastEB;
@@ -353,30 +355,28 @@ __global__ void __launch_bounds__(256) mlp_bwd_last_kernel(const ConvBwdParams p
 #pragma unroll
         for (int i = 0; i < KP; ++i) {
           const T hv = hs2[el * HP + tk + 8 * i];
-          accw[i][0] = fma(hv, d0, accw[i][0]);
-          accw[i][1] = fma(hv, d1, accw[i][1]);
-          accw[i][2] = fma(hv, d2, accw[i][2]);
-          accw[i][3] = fma(hv, d3, accw[i][3]);
+          fma_pair(hv, d0, d1, accw[i][0]);
+          fma_pair(hv, d2, d3, accw[i][1]);
         }
       }
     }
     // dH[e][k] (this column group) = sum_c dw[e][c] W[k][c] / sqrt(H)
     {
-      T acch[KD];
+      P acch[KD / 2];
 #pragma unroll
-      for (int i = 0; i < KD; ++i) acch[i] = T(0);
+      for (int i = 0; i < KD / 2; ++i) acch[i].x = acch[i].y = T(0);
       const T* dr = dws + te * DS;
       for (int c = 0; c < kLastCW; ++c) {
         const T dv = dr[c];
         const T* wr = WlT + c * HP + kq * KD;
 #pragma unroll
-        for (int i = 0; i < KD; ++i) acch[i] = fma(dv, wr[i], acch[i]);
+        for (int i = 0; i < KD / 2; ++i) fma_pair(dv, wr[2 * i], wr[2 * i + 1], acch[i]);
       }
       if (te < ne) {
         T* dh = static_cast<T*>(p.DHP) + ((size_t)cg * p.E + (e0 + te)) * H;
 #pragma unroll
         for (int i = 0; i < KD; ++i)
-          if (kq * KD + i < H) dh[kq * KD + i] = acch[i];
+          if (kq * KD + i < H) dh[kq * KD + i] = (i & 1) ? acch[i >> 1].y : acch[i >> 1].x;
       }
     }
   }
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_last_kernel(const ConvBwdParams p
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = tc * 4 + j;
-        if (c < ncol) part[(size_t)k * Wn + cbase + c] = accw[i][j];
+        if (c < ncol) part[(size_t)k * Wn + cbase + c] = (j & 1) ? accw[i][j >> 1].y : accw[i][j >> 1].x;
       }
     }
   }

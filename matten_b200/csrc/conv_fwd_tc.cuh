@@ -315,9 +315,9 @@ __global__ void __launch_bounds__(kPrepThreads) edge_prepare_kernel(const ConvTc
       const int fi = p.sizes[li], fo = p.sizes[li + 1];
 #pragma unroll
       for (int j = 0; j < kTcK; ++j) hrow[j] = h[j];
-      float a[kTcK];
+      float2 a[kTcK / 2];  // output pairs: one FFMA2 (broadcast h[k]) per pair
 #pragma unroll
-      for (int j = 0; j < kTcK; ++j) a[j] = 0.f;
+      for (int j = 0; j < kTcK / 2; ++j) a[j] = make_float2(0.f, 0.f);
       const float* W = sW[li];
 #pragma unroll 4
       for (int k = 0; k < fi; ++k) {
@@ -326,14 +326,15 @@ __global__ void __launch_bounds__(kPrepThreads) edge_prepare_kernel(const ConvTc
 #pragma unroll
         for (int j4 = 0; j4 < kTcK / 4; ++j4) {
           const float4 w4 = wr[j4];
-          a[4 * j4 + 0] = fmaf(hk, w4.x, a[4 * j4 + 0]);
-          a[4 * j4 + 1] = fmaf(hk, w4.y, a[4 * j4 + 1]);
-          a[4 * j4 + 2] = fmaf(hk, w4.z, a[4 * j4 + 2]);
-          a[4 * j4 + 3] = fmaf(hk, w4.w, a[4 * j4 + 3]);
+          fma_pair(hk, w4.x, w4.y, a[2 * j4]);
+          fma_pair(hk, w4.z, w4.w, a[2 * j4 + 1]);
         }
       }
 #pragma unroll
-      for (int j = 0; j < kTcK; ++j) h[j] = (j < fo) ? apply_act<float>(p.act, a[j]) * p.act_cst : 0.f;
+      for (int j = 0; j < kTcK; ++j) {
+        const float aj = (j & 1) ? a[j >> 1].y : a[j >> 1].x;
+        h[j] = (j < fo) ? apply_act<float>(p.act, aj) * p.act_cst : 0.f;
+      }
     }
     // planes [3][4][E][8]
 #pragma unroll

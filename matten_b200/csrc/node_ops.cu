@@ -122,11 +122,12 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
 
   const int tcn = COLS >> 2;  // thread columns
   const int tc = tid % tcn, tr = tid / tcn;
-  T acc[4][4];
+  using P = typename pair_of<T>::type;  // column pairs: one FFMA2 per pair in fp32
+  P acc[4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    for (int j = 0; j < 2; ++j) { acc[i][j].x = T(0); acc[i][j].y = T(0); }
 
   for (int u0 = 0; u0 < mi; u0 += KC) {
     const int ku = min(KC, mi - u0);
@@ -160,9 +161,10 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
       lin_ld4<T>(xsT + uu * XS + tr * 4, a);   // 16-byte aligned: XS and COLS are multiples of 4
       lin_ld4<T>(ws + uu * COLS + tc * 4, bb);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+      for (int i = 0; i < 4; ++i) {
+        fma_pair(a[i], bb[0], bb[1], acc[i][0]);
+        fma_pair(a[i], bb[2], bb[3], acc[i][1]);
+      }
     }
     __syncthreads();
   }
@@ -171,7 +173,10 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ot[(tr * 4 + i) * OS + tc * 4 + j] = acc[i][j] * scale;
+    for (int j = 0; j < 2; ++j) {
+      ot[(tr * 4 + i) * OS + tc * 4 + 2 * j] = acc[i][j].x * scale;
+      ot[(tr * 4 + i) * OS + tc * 4 + 2 * j + 1] = acc[i][j].y * scale;
+    }
   __syncthreads();
   // coalesced write: per node the (w, m) range is contiguous
   const int span = ncols * d;

@@ -54,11 +54,12 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const WgParams p) {
   const int tid = threadIdx.x, tu = tid >> 4, tw = tid & 15;  // 16 x 16 threads, 4 x 4 outputs each
   const T* __restrict__ X = static_cast<const T*>(p.x);
   const T* __restrict__ G = static_cast<const T*>(p.g);
-  T acc[4][4];
+  using P = typename pair_of<T>::type;  // column pairs: one FFMA2 per pair in fp32
+  P acc[4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    for (int j = 0; j < 2; ++j) acc[i][j].x = acc[i][j].y = T(0);
   const int npt = max(1, kWgRows / d);  // nodes per step (rows = nodes x d <= kWgRows when d <= kWgRows)
   for (int64_t nb = n_begin; nb < n_end; nb += npt) {
     const int tn = (int)imin64(npt, n_end - nb);
@@ -85,9 +86,10 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const WgParams p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) bb[j] = gs[r][tw * 4 + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+      for (int i = 0; i < 4; ++i) {
+        fma_pair(a[i], bb[0], bb[1], acc[i][0]);
+        fma_pair(a[i], bb[2], bb[3], acc[i][1]);
+      }
     }
   }
   const T scale = T(p.scale[b]);
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const WgParams p) {
     for (int j = 0; j < 4; ++j) {
       const int w = w0 + tw * 4 + j;
       if (tw * 4 + j >= nw) continue;
-      part[(size_t)p.w_off[b] + ((size_t)u * p.S + s) * mo + w] = acc[i][j] * scale;
+      part[(size_t)p.w_off[b] + ((size_t)u * p.S + s) * mo + w] = ((j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x) * scale;
     }
   }
 }
