@@ -1,4 +1,6 @@
 // Host side of mt_conv_bwd (include/matten_b200.h): workspace carve-up and the K0..K4 launches.
+#include <stdlib.h>
+
 #include "conv_bwd.cuh"
 
 namespace mt {
@@ -126,7 +128,10 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
     const size_t fixed = (size_t)p.num_paths * 16;
     // resident CTAs per SM the register budget allows (launch bounds of conv_bwd_kernel) -> shared-memory budget per CTA:
     // the kernel alternates staging / GEMM / contraction phases between barriers, so more small CTAs hide more of it
-    const int per_sm_regs = sizeof(T) == 4 ? 3 : 2;
+    const char* env_t = getenv("MT_BWD_THREADS");
+    const char* env_c = getenv("MT_BWD_CTAS");
+    const int threads1 = (env_t && *env_t) ? atoi(env_t) : 128;  // more, smaller CTAs hide the phase barriers better (r1 sweep)
+    const int per_sm_regs = (env_c && *env_c) ? atoi(env_c) : ((sizeof(T) == 4 ? 3 : 2) * (256 / threads1));
     const size_t budget = (size_t)(227 * 1024) / per_sm_regs - 1024;
     int EC = 32, TN = 1;
     size_t smem = 0;
@@ -157,7 +162,7 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)kNumSMs * per_sm;
     if (grid > tiles) grid = tiles;
-    conv_bwd_kernel<T><<<(int)grid, 256, smem, st>>>(p);
+    conv_bwd_kernel<T><<<(int)grid, threads1, smem, st>>>(p);
     MT_LAUNCH_OK();
   }
   // per-sender sum of the per-edge input gradients
