@@ -25,10 +25,6 @@ def launch_count() -> int:
 CONV_EVENTS = None
 
 
-def _bump(n: int = 1):
-    pass
-
-
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return MT_F32
@@ -90,7 +86,6 @@ def edge_vectors(pos, edge_index, edge_cell_shift=None, cell=None, batch=None, f
     ln = torch.empty((E,), dtype=pos.dtype, device=pos.device) if want_len else None
     check(lib.mt_edge_vectors(_dt(pos), _p(pos), _p(edge_index), _p(edge_cell_shift), _p(cell),
                               _p(batch) if B > 1 else None, N, E, B, _p(vec), _p(ln), _p(flag), _stream(pos)))
-    _bump()
     return vec, ln
 
 
@@ -100,7 +95,6 @@ def edge_sh(edge_vec, lmax: int, normalize: bool = True):
     E = edge_vec.shape[0]
     out = torch.empty((E, (lmax + 1) ** 2), dtype=edge_vec.dtype, device=edge_vec.device)
     check(lib.mt_edge_sh(_dt(edge_vec), _p(edge_vec), E, lmax, int(normalize), _p(out), _stream(edge_vec)))
-    _bump()
     return out
 
 
@@ -114,7 +108,6 @@ def edge_radial(edge_len, mode: int, num_basis: int, start: float, end: float, c
     out = torch.empty((E, num_basis), dtype=edge_len.dtype, device=edge_len.device)
     check(lib.mt_edge_radial(_dt(edge_len), _p(edge_len), E, mode, num_basis, float(start), float(end),
                              int(cutoff), float(poly_p), _p(bessel_w), _p(out), _stream(edge_len)))
-    _bump()
     return out
 
 
@@ -155,8 +148,6 @@ def csr_by_key(keys, num_keys: int, want_perm: bool = True, flag=None):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=keys.device)
     check(lib.mt_csr_by_key(_p(keys), E, num_keys, _p(rowptr), _p(perm), _p(ws), nbytes, _p(flag),
                             _stream(keys)))
-    # launches: init + per pass (hist, scan>=1, scatter) + rowptr  (approximate lower bound)
-    _bump(3 if not want_perm else 2 + 3 * max(1, ((max(num_keys, 2) - 1).bit_length() + 7) // 8))
     return rowptr, perm
 
 
@@ -166,7 +157,6 @@ def gather_i64_to_i32(src, perm=None):
     n = perm.shape[0] if perm is not None else src.shape[0]
     out = torch.empty(n, dtype=torch.int32, device=src.device)
     check(lib.mt_gather_i64_to_i32(_p(src), _p(perm), n, _p(out), _stream(src)))
-    _bump()
     return out
 
 
@@ -174,7 +164,6 @@ def check_sorted(keys, flag):
     lib = _lib.load()
     keys = _req(keys, "keys", torch.int64)
     check(lib.mt_check_sorted(_p(keys), keys.shape[0], _p(flag), _stream(keys)))
-    _bump()
 
 
 def species_embed(atomic_numbers, species_index, lut, min_z: int, max_z: int, num_species: int,
@@ -199,7 +188,6 @@ def species_embed(atomic_numbers, species_index, lut, min_z: int, max_z: int, nu
     check(lib.mt_species_embed(_dt(lin_w), _p(atomic_numbers), int(z_given), _p(lut), int(min_z), int(max_z),
                                num_species, dim, _p(lin_w), _p(lin_b), N, _p(species_index), _p(attrs),
                                _p(feats), _p(flag), _stream(lin_w)))
-    _bump()
     return species_index, attrs, feats
 
 
@@ -336,7 +324,6 @@ def linear_fwd(h: LinPlanHandle, x, weight, species_perm=None, species_ptr=None,
         out = torch.empty((N, h.out_dim), dtype=x.dtype, device=x.device)
     check(lib.mt_linear_fwd(_dt(x), h.arr, h.n, h.in_dim, h.out_dim, h.S, _p(x2), _p(weight), _p(species_perm),
                             _p(species_ptr), int(accumulate), _p(out), N, _stream(x)))
-    _bump()
     return out.reshape(lead + (h.out_dim,))
 
 
@@ -409,7 +396,6 @@ def gate_fwd(x, in_dim: int, out_dim: int, src_idx, gate_idx, act_id, act_cst, a
     out = torch.empty(lead + (out_dim,), dtype=x.dtype, device=x.device)
     check(lib.mt_gate_fwd(_dt(x), _p(x), in_dim, out_dim, _p(src_idx), _p(gate_idx), _p(act_id), _p(act_cst),
                           _p(affine_a), _p(affine_b), _p(out), N, _stream(x)))
-    _bump()
     return out
 
 
@@ -424,7 +410,6 @@ def segment_reduce(x, ptr, reduce: str = "sum"):
     dim = x.shape[1]
     out = torch.empty((B, dim), dtype=x.dtype, device=x.device)
     check(lib.mt_segment_reduce(_dt(x), _p(x), _p(ptr), dim, B, _MODES[reduce], _p(out), _stream(x)))
-    _bump()
     return out
 
 
