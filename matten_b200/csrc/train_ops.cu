@@ -31,11 +31,15 @@ struct WgParams {
   int64_t N;
 };
 
-// CTA <-> (block b, species s, u tile, w tile, split): partial dW tile over the split's node range
+// CTA <-> (block b, species s, u tile, w tile, split): partial dW tile over the split's node range.
+// The (u, w) tile is at most 64 x 64 but follows the block (the l = 2 irreps have 4 output channels): a thread owns
+// 4 x 4 outputs, tun x tcn threads cover the tile, and the remaining threads form KG - 1 more "row groups" that take
+// every KG-th staged row; the row groups are summed in a fixed order at the end (deterministic).
 template <typename T>
 __global__ void __launch_bounds__(256) linear_wgrad_kernel(const WgParams p) {
-  __shared__ T xs[kWgRows][kWgTile + 1];
-  __shared__ T gs[kWgRows][kWgTile + 1];
+  __shared__ __align__(16) T smem_w[2 * kWgRows * (kWgTile + 1)];
+  T(*xs)[kWgTile + 1] = reinterpret_cast<T(*)[kWgTile + 1]>(smem_w);
+  T(*gs)[kWgTile + 1] = reinterpret_cast<T(*)[kWgTile + 1]>(smem_w + kWgRows * (kWgTile + 1));
   int b = 0;
   while (b + 1 < p.num_blocks && (int)blockIdx.x >= p.cta_begin[b + 1]) ++b;
   int local = blockIdx.x - p.cta_begin[b];
@@ -51,7 +55,13 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const WgParams p) {
   const int64_t n_begin = lo + cnt * split / p.splits, n_end = lo + cnt * (split + 1) / p.splits;
   const int u0 = uti * kWgTile, w0 = wti * kWgTile;
   const int nu = min(kWgTile, mi - u0), nw = min(kWgTile, mo - w0);
-  const int tid = threadIdx.x, tu = tid >> 4, tw = tid & 15;  // 16 x 16 threads, 4 x 4 outputs each
+  const int tun = (nu + 3) >> 2, tcn = (nw + 3) >> 2;  // threads along u / w
+  const int per = tun * tcn;
+  const int KG = 256 / per;                            // row groups (per <= 256)
+  const int tid = threadIdx.x;
+  const int kg = tid / per, rem = tid - kg * per;
+  const int tu = rem / tcn, tw = rem - tu * tcn;
+  const bool active = kg < KG;
   const T* __restrict__ X = static_cast<const T*>(p.x);
   const T* __restrict__ G = static_cast<const T*>(p.g);
   using P = typename pair_of<T>::type;  // column pairs: one FFMA2 per pair in fp32
@@ -60,10 +70,9 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const WgParams p) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) acc[i][j].x = acc[i][j].y = T(0);
-  const int npt = max(1, kWgRows / d);  // nodes per step (rows = nodes x d <= kWgRows when d <= kWgRows)
+  const int npt = max(1, kWgRows / d);  // nodes per step (rows = nodes x d <= kWgRows: d <= 9)
   for (int64_t nb = n_begin; nb < n_end; nb += npt) {
     const int tn = (int)imin64(npt, n_end - nb);
-    // d may exceed kWgRows (l = 16+ never happens: d <= 9) -> rows = tn * d <= kWgRows
     __syncthreads();
     for (int t = tid; t < kWgRows * kWgTile; t += blockDim.x) {
       const int r = t / kWgTile, c = t - r * kWgTile;
@@ -79,31 +88,42 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const WgParams p) {
     }
     __syncthreads();
     const int rows = tn * d;
-    for (int r = 0; r < rows; ++r) {
-      T a[4], bb[4];
+    if (active) {
+      for (int r = kg; r < rows; r += KG) {
+        T a[4], bb[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = xs[r][tu * 4 + i];
+        for (int i = 0; i < 4; ++i) a[i] = xs[r][tu * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bb[j] = gs[r][tw * 4 + j];
+        for (int j = 0; j < 4; ++j) bb[j] = gs[r][tw * 4 + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        fma_pair(a[i], bb[0], bb[1], acc[i][0]);
-        fma_pair(a[i], bb[2], bb[3], acc[i][1]);
+        for (int i = 0; i < 4; ++i) {
+          fma_pair(a[i], bb[0], bb[1], acc[i][0]);
+          fma_pair(a[i], bb[2], bb[3], acc[i][1]);
+        }
       }
     }
   }
+  // fixed-order sum over the row groups: red[kg][output] aliases the staging buffers (<= 256 x 16 elements)
+  __syncthreads();
+  T* red = smem_w;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        red[(size_t)kg * per * 16 + rem * 16 + i * 4 + j] = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
+  }
+  __syncthreads();
   const T scale = T(p.scale[b]);
   T* part = static_cast<T*>(p.part) + (size_t)split * p.numel;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int u = u0 + tu * 4 + i;
-    if (tu * 4 + i >= nu) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int w = w0 + tw * 4 + j;
-      if (tw * 4 + j >= nw) continue;
-      part[(size_t)p.w_off[b] + ((size_t)u * p.S + s) * mo + w] = ((j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x) * scale;
-    }
+  for (int t = tid; t < per * 16; t += blockDim.x) {
+    const int rm = t >> 4, ij = t & 15;
+    const int tu2 = rm / tcn, tw2 = rm - tu2 * tcn;
+    const int ul = tu2 * 4 + (ij >> 2), wl = tw2 * 4 + (ij & 3);
+    if (ul >= nu || wl >= nw) continue;
+    T sum = T(0);
+    for (int q = 0; q < KG; ++q) sum += red[(size_t)q * per * 16 + t];
+    part[(size_t)p.w_off[b] + ((size_t)(u0 + ul) * p.S + s) * mo + (w0 + wl)] = sum * scale;
   }
 }
 
