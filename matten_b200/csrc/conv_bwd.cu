@@ -41,9 +41,9 @@ static BwdLayout bwd_layout(const mt_conv_plan* plan, size_t es, int64_t E) {
   for (int i = 0; i < nl; ++i) hmax = plan->mlp_sizes[i] > hmax ? plan->mlp_sizes[i] : hmax;
   L.rs = hmax + 1;
   L.hid_eb = kHidEBMax;
-  while (L.hid_eb > 16 && ((size_t)3 * L.hid_eb * L.rs + (size_t)L.rs * L.rs + hid) * es > 72 * 1024) L.hid_eb >>= 1;
+  while (L.hid_eb > 16 && ((size_t)3 * L.hid_eb * L.rs + (size_t)L.rs * L.rs + hid) * es > 36 * 1024) L.hid_eb >>= 1;
   const int64_t chunks3 = ceil_div<int64_t>(E, L.hid_eb);
-  L.grid3 = (int)(chunks3 < 2 * kNumSMs ? (chunks3 > 0 ? chunks3 : 1) : 2 * kNumSMs);
+  L.grid3 = (int)(chunks3 < 6 * kNumSMs ? (chunks3 > 0 ? chunks3 : 1) : 6 * kNumSMs);  // small tiles: 6 CTAs per SM
   L.dw_off = o;
   o += align256((size_t)E * Wn * es);
   L.dxe_off = o;

@@ -26,7 +26,7 @@ constexpr int kBwdMaxH = 64;     // largest MLP layer input/hidden size the back
 constexpr int kBwdET = 8;        // edges per register pass of phase A (chunk_edges is a multiple of it)
 constexpr int kLastEB = 64;      // edges per chunk of K2
 constexpr int kLastCW = 128;     // weight columns per CTA column group of K2
-constexpr int kHidEBMax = 128;   // edges per chunk of K0 / K3 (halved until the tiles fit: ConvBwdParams::hid_eb)
+constexpr int kHidEBMax = 64;    // edges per chunk of K0 / K3 (halved until the tiles fit: ConvBwdParams::hid_eb)
 
 struct ConvBwdParams {
   int x_dim, y_dim, out_dim, Wn;
