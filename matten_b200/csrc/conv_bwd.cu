@@ -118,7 +118,7 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
       cfg0 = smem0;
     }
     const int64_t chunks = ceil_div<int64_t>(E, p.hid_eb);
-    const int grid0 = (int)(chunks < 4 * kNumSMs ? chunks : 4 * kNumSMs);
+    const int grid0 = (int)(chunks < 12 * kNumSMs ? chunks : 12 * kNumSMs);
     edge_hidden_kernel<T><<<grid0, 256, smem0, st>>>(p);
     MT_LAUNCH_OK();
   }
