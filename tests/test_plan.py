@@ -126,3 +126,44 @@ def test_gate_plan_irreps():
                  {1: "sigmoid", -1: "tanh"})
     assert str(g.irreps_in) == "32x0o+78x0e+16x1o+16x1e+4x2o+4x2e+2x3o+2x3e+2x4e"
     assert g.irreps_in.dim == 292 and g.irreps_out.dim == 246
+
+
+@pytest.mark.parametrize("x_ir,sh_lmax,out_ir", [
+    ("16x0e", 2, "52x0e+16x1o+4x2e"),
+    ("32x0o+32x0e+16x1o+16x1e+4x2o+4x2e", 2, "32x0o+32x0e+16x1o+16x1e+4x2o+4x2e"),
+    ("32x0o+32x0e+16x1o+16x1e+4x2o+4x2e+2x3o+2x3e+2x4e", 4, "32x0o+32x0e+16x1o+16x1e+4x2o+4x2e+2x3o+2x3e+2x4e"),
+    ("20x0e+12x1o+5x2e+3x1e", 2, "20x0e+12x1o+5x2e+3x1e"),
+])
+def test_backward_tables_cover_every_channel_and_weight_column_once(x_ir, sh_lmax, out_ir):
+    """Tables of mt_conv_bwd (plan._build_bwd): every element of the x row belongs to exactly one (item, lane) --
+    the gradient of the gathered row is written, never accumulated -- and every weight column / output slot of the
+    forward plan is reached through exactly one (item, lane, path)."""
+    from matten_b200 import o3
+    from matten_b200.codegen.gen_tables import cg_type_id
+    from matten_b200.plan import UVUPlan
+
+    pl = UVUPlan(o3.Irreps(x_ir), o3.Irreps.spherical_harmonics(sh_lmax), o3.Irreps(out_ir))
+    hdr, lanes, paths = pl.bw_item_hdr.tolist(), pl.bw_lane_tab.tolist(), pl.bw_path_tab.tolist()
+    tid2l = {cg_type_id(p.l1, p.l2, p.l3): (p.l1, p.l2, p.l3) for p in pl.paths}
+    x_seen = [0] * pl.x_dim
+    w_seen = [0] * pl.weight_numel
+    out_seen = [0] * pl.out_dim
+    for (l1, cpw, first, count), lt in zip(hdr, lanes):
+        assert 32 % cpw == 0
+        for lane in range(cpw):  # the other lanes repeat these channels on further edge phases
+            u, xoff = lt[lane]
+            if u < 0:
+                continue
+            for m in range(2 * l1 + 1):
+                x_seen[xoff + m] += 1
+            for tid, wcol0, yoff, ooff0 in paths[first:first + count]:
+                a, b, c = tid2l[tid]
+                assert a == l1 and yoff == b * b
+                w_seen[wcol0 + u] += 1
+                for m in range(2 * c + 1):
+                    out_seen[ooff0 + u * (2 * c + 1) + m] += 1
+        for lane in range(cpw, 32):
+            assert lt[lane] == lt[lane % cpw]
+    assert x_seen == [1] * pl.x_dim
+    assert w_seen == [1] * pl.weight_numel
+    assert out_seen == [1] * pl.out_dim
