@@ -367,31 +367,29 @@ __device__ __forceinline__ void tc_unit(uint32_t taddr, const float* __restrict_
   MT_TMEM_LD_X4(taddr, c0, c1, c2, c3);
   MT_TMEM_LD_WAIT(c0, c1, c2, c3);
   if (cpw == 32) {
-    // FFMA2 pays for the light contractions (l1 <= 1: few distinct coefficients); for l1 = 2 the packed version
-    // needs a register per coefficient pair and measured > 1.5x slower (r1 sweep, lmax 2 / mul 32) -> scalar there
-    if constexpr (L1 <= 1) {
     // lane == TMEM row: every lane walks all columns, two edges per iteration packed into FFMA2 / FMUL2 (edge a in
     // the low half, edge b in the high half of every register pair); the two partial sums are added at the end
     constexpr int D3 = 2 * L3 + 1;
     f2 acc2[D3];
 #pragma unroll
     for (int m = 0; m < D3; ++m) acc2[m] = f2(0.f, 0.f);
+    auto two_edges = [&](const f2 w2) {
+      f2 x2[D1], y2[D2];
+#pragma unroll
+      for (int m = 0; m < D1; ++m) x2[m] = f2(xp[m], xp[xstride + m]);
+#pragma unroll
+      for (int m = 0; m < D2; ++m) y2[m] = f2(yp[m], yp[ystride + m]);
+      CG<L1, L2, L3>::template fwd<f2>(x2, y2, w2, acc2);
+      xp += 2 * xstride;
+      yp += 2 * ystride;
+    };
 #pragma unroll 1
     for (int g = 0; g < ngrp; ++g) {
       const bool more = g + 1 < ngrp;
       if (more) MT_TMEM_LD_X4(taddr + (uint32_t)(4 * g + 4), n0, n1, n2, n3);  // prefetch the next 4 columns
+      // (rolled on purpose: straight-line code for the 4 columns of a group measured 4 % slower -- instruction fetch)
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const f2 w2(__uint_as_float(h ? c2 : c0), __uint_as_float(h ? c3 : c1));
-        f2 x2[D1], y2[D2];
-#pragma unroll
-        for (int m = 0; m < D1; ++m) x2[m] = f2(xp[m], xp[xstride + m]);
-#pragma unroll
-        for (int m = 0; m < D2; ++m) y2[m] = f2(yp[m], yp[ystride + m]);
-        CG<L1, L2, L3>::template fwd<f2>(x2, y2, w2, acc2);
-        xp += 2 * xstride;
-        yp += 2 * ystride;
-      }
+      for (int h = 0; h < 2; ++h) two_edges(f2(__uint_as_float(h ? c2 : c0), __uint_as_float(h ? c3 : c1)));
       if (more) {
         MT_TMEM_LD_WAIT(n0, n1, n2, n3);
         c0 = n0; c1 = n1; c2 = n2; c3 = n3;
@@ -399,37 +397,6 @@ __device__ __forceinline__ void tc_unit(uint32_t taddr, const float* __restrict_
     }
 #pragma unroll
     for (int m = 0; m < D3; ++m) acc[m] += acc2[m].v.x + acc2[m].v.y;
-    } else {
-    // lane == TMEM row: every lane walks all columns, two edges per iteration packed into FFMA2 / FMUL2 (edge a in
-    // the low half, edge b in the high half of every register pair); the two partial sums are added at the end
-    constexpr int D3 = 2 * L3 + 1;
-    f2 acc2[D3];
-#pragma unroll
-    for (int m = 0; m < D3; ++m) acc2[m] = f2(0.f, 0.f);
-#pragma unroll 1
-    for (int g = 0; g < ngrp; ++g) {
-      const bool more = g + 1 < ngrp;
-      if (more) MT_TMEM_LD_X4(taddr + (uint32_t)(4 * g + 4), n0, n1, n2, n3);  // prefetch the next 4 columns
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const f2 w2(__uint_as_float(h ? c2 : c0), __uint_as_float(h ? c3 : c1));
-        f2 x2[D1], y2[D2];
-#pragma unroll
-        for (int m = 0; m < D1; ++m) x2[m] = f2(xp[m], xp[xstride + m]);
-#pragma unroll
-        for (int m = 0; m < D2; ++m) y2[m] = f2(yp[m], yp[ystride + m]);
-        CG<L1, L2, L3>::template fwd<f2>(x2, y2, w2, acc2);
-        xp += 2 * xstride;
-        yp += 2 * ystride;
-      }
-      if (more) {
-        MT_TMEM_LD_WAIT(n0, n1, n2, n3);
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < D3; ++m) acc[m] += acc2[m].v.x + acc2[m].v.y;
-    }
   } else {
     // packed small types: lane = (column j, phase ph); phase ph takes the columns == ph (mod nphase) of every
     // group and fetches its weight from the lane that owns the column's TMEM row
