@@ -105,9 +105,9 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
       MT_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     configured[vi] = L.total;
   }
-  if (NE == 256) conv_fwd_tc_kernel<256><<<(unsigned)grid, kTcThreads, L.total, st>>>(p);
-  else if (NE == 128) conv_fwd_tc_kernel<128><<<(unsigned)grid, kTcThreads, L.total, st>>>(p);
-  else conv_fwd_tc_kernel<64><<<(unsigned)grid, kTcThreads, L.total, st>>>(p);
+  if (NE == 256) conv_fwd_tc_kernel<256><<<(unsigned)grid, tc_threads(256), L.total, st>>>(p);
+  else if (NE == 128) conv_fwd_tc_kernel<128><<<(unsigned)grid, tc_threads(128), L.total, st>>>(p);
+  else conv_fwd_tc_kernel<64><<<(unsigned)grid, tc_threads(64), L.total, st>>>(p);
   MT_LAUNCH_OK();
   *used = 1;
   return MT_OK;

@@ -38,9 +38,12 @@ namespace mt {
 __host__ __device__ constexpr int tc_chunk_cols(int MT) { return MT <= 1 ? 256 : (MT == 2 ? 128 : 64); }
 constexpr int kTcK = 32;              // padded size of the last hidden layer == MMA K total
 constexpr int kTcProducerWarps = 4;   // warp 0: chunks + plane / sh copies, warp 1: MMA issue, warps 2-3: x-row copies
-constexpr int kTcConsumerWarps = 28;  // 7 per TMEM quarter: every warp is a latency-bound dependent chain, so
-                                      // throughput comes from the warp count (1024 threads, 64 registers each)
-constexpr int kTcThreads = 32 * (kTcProducerWarps + kTcConsumerWarps);
+// consumer warps per chunk width (a multiple of 4: warp w reads TMEM quarter w % 4).  Fewer than the 28 that fill a
+// 1024-thread CTA: with 16 (4 per quarter / scheduler) the kernel gets 92 registers per thread and each scheduler's
+// instruction stream stays resident -- measured on the bench layers (ms per call, layers 1..3), 28 warps: 1.19 / 1.40 /
+// 1.47, 24: 1.03 / 1.22 / 1.24, 20: 1.16 / 1.33 / 1.31, 16: 1.09 / 1.11 / 1.18, 12: 1.25 / 1.30 / 1.36.
+__host__ __device__ constexpr int tc_consumer_warps(int NE) { return NE == 128 ? 24 : 16; }
+__host__ __device__ constexpr int tc_threads(int NE) { return 32 * (kTcProducerWarps + tc_consumer_warps(NE)); }
 constexpr int kTcMaxTiles = 4;        // M tiles of 128 rows -> <= 512 weight-column rows
 constexpr int kTcMaxSub = 64;         // sub-items per plan
 constexpr int kTcMaxNodes = 16;       // receiver nodes per chunk
@@ -438,7 +441,8 @@ __device__ __forceinline__ void tc_unit(uint32_t taddr, const float* __restrict_
 }
 
 template <int NE>
-__global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const ConvTcParams p) {
+__global__ void __launch_bounds__(tc_threads(NE), 1) conv_fwd_tc_kernel(const ConvTcParams p) {
+  constexpr int kTcConsumerWarps = tc_consumer_warps(NE), kTcThreads = tc_threads(NE);
   extern __shared__ __align__(128) unsigned char smem[];  // no swizzle: descriptors need 16 B alignment
   __shared__ uint64_t bar_full[2], bar_empty[2], bar_go[2], bar_bready, bar_bfree;
   __shared__ uint32_t s_tmem_base;
