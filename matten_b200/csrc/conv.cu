@@ -97,13 +97,19 @@ static int conv_fwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
   for (int i = 0; i + 1 < p.nl; ++i) hidden_w += (size_t)p.sizes[i] * p.sizes[i + 1];
   const size_t smem = (size_t)EC * per_edge + hidden_w * sizeof(T);
   MT_REQUIRE(smem <= 227 * 1024, "conv tile needs %zu bytes of shared memory", smem);
-  const int threads = env_int("MT_CONV_THREADS", 256);
+  // Resident warps per SM follow the number of contraction types the plan can touch (instruction-cache footprint: every
+  // warp runs the inlined code of ONE (l1,l2,l3) type).  r1 sweep, natural irreps, 1e6 edges, fp32, ms per call with
+  // (CTAs/SM x threads) = (3 x 256) / (2 x 256) / (2 x 128): sh lmax 2: 4.6 / 5.5 / 8.7; lmax 3: 16.3 / 15.2 / 25.7;
+  // lmax 4: 45.0 / 36.5 / 17.0.
+  const int sh_lmax = p.y_dim >= 25 ? 4 : (p.y_dim >= 16 ? 3 : 2);
+  const int threads = env_int("MT_CONV_THREADS", (sizeof(T) == 4 && sh_lmax >= 4) ? 128 : 256);
   MT_REQUIRE(threads >= 32 && threads <= 256 && threads % 32 == 0, "MT_CONV_THREADS must be 32..256");
   int64_t tiles = ceil_div<int64_t>(N, p.tile_nodes);
   int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int reg_limit = sizeof(T) == 4 ? (HP <= 32 ? 3 : 2) : 1;  // conv_fwd_min_blocks<T, HP>()
   if (ctas_per_sm > reg_limit) ctas_per_sm = reg_limit;
+  if (sizeof(T) == 4 && sh_lmax >= 3 && ctas_per_sm > 2) ctas_per_sm = 2;
   ctas_per_sm = env_int("MT_CONV_CTAS_PER_SM", ctas_per_sm);
   int64_t grid = (int64_t)kNumSMs * ctas_per_sm;
   if (grid > tiles) grid = tiles;
