@@ -167,3 +167,55 @@ def test_backward_tables_cover_every_channel_and_weight_column_once(x_ir, sh_lma
     assert x_seen == [1] * pl.x_dim
     assert w_seen == [1] * pl.weight_numel
     assert out_seen == [1] * pl.out_dim
+
+
+@pytest.mark.parametrize("x_ir,out_ir", [
+    ("16x0e", "52x0e+16x1o+4x2e"),
+    ("32x0e+16x1o+4x2e", "72x0e+16x1o+16x1e+4x2o+4x2e"),
+    ("32x0o+32x0e+16x1o+16x1e+4x2o+4x2e", "32x0o+32x0e+16x1o+16x1e+4x2o+4x2e"),
+    ("20x0e+12x1o+4x2e+4x1e", "20x0e+12x1o+4x2e+4x1e"),
+    ("32x0e+32x1o+32x2e", "32x0e+32x1o+32x2e"),
+])
+def test_tcgen05_tables_place_every_weight_column_on_one_tmem_lane(x_ir, out_ir):
+    """Tables of the tensor-core path (plan._build_tc): every weight column of the tensor product sits on exactly one
+    row of the MMA A operand (= one TMEM lane of one tile); a sub-item's lanes read the rows of its own 32-lane
+    quarter; every quarter holds at most num_tiles groups; the slot tables address the same x / sh / out elements as
+    the forward items of the FMA-pipe kernel."""
+    from matten_b200 import o3
+    from matten_b200.plan import UVUPlan
+
+    pl = UVUPlan(o3.Irreps(x_ir), o3.Irreps.spherical_harmonics(2), o3.Irreps(out_ir))
+    assert 1 <= pl.tc_num_tiles <= 4
+    rows = pl.tc_row_wcol.tolist()
+    assert len(rows) == pl.tc_num_tiles * 128
+    used = sorted(r for r in rows if r >= 0)
+    assert used == list(range(pl.weight_numel))  # each weight column exactly once
+    ref = {}
+    for (tid, cpw), slots in zip(pl.item_hdr.tolist(), pl.slot_tab.tolist()):
+        for wcol, xoff, yoff, ooff in slots:
+            if wcol >= 0:
+                ref[wcol] = (tid, xoff, yoff, ooff)
+    hdr, slot = pl.tc_sub_hdr.tolist(), pl.tc_sub_slot.tolist()
+    per_q_tiles = [set() for _ in range(4)]
+    seen = set()
+    for (tid, cpw, lane0, tile, q, d3, _, _), sl in zip(hdr, slot):
+        assert cpw in (8, 16, 32) and 0 <= lane0 and lane0 + cpw <= 32 and 0 <= tile < pl.tc_num_tiles
+        per_q_tiles[q].add(tile)
+        for j in range(cpw):
+            xoff, yoff, ooff, valid = sl[j]
+            wcol = rows[tile * 128 + q * 32 + lane0 + j]
+            assert (wcol >= 0) == bool(valid)
+            if valid:
+                assert ref[wcol] == (tid, xoff, yoff, ooff)
+                assert wcol not in seen
+                seen.add(wcol)
+        for lane in range(cpw, 32):  # further edge phases repeat the columns
+            assert sl[lane] == sl[lane % cpw]
+    assert len(seen) == pl.weight_numel
+    assert all(len(t) <= pl.tc_num_tiles for t in per_q_tiles)
+    assert sum(pl.tc_q_count) == pl.tc_num_sub
+    ql = pl.tc_q_list.tolist()
+    listed = sorted(s for q in range(4) for s in ql[q][:pl.tc_q_count[q]])
+    assert listed == list(range(pl.tc_num_sub))
+    for q in range(4):
+        assert all(hdr[s][4] == q for s in ql[q][:pl.tc_q_count[q]])
