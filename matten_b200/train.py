@@ -85,3 +85,29 @@ class Trainer:
             torch.distributed.all_reduce(self.opt.flat_g, group=self.pg)
         self.opt.step(grad_scale=1.0 / self.world)
         return loss.detach()
+
+
+    @torch.no_grad()
+    def evaluate(self, batches) -> Dict[str, float]:
+        """Validation pass (reference ``validation_step`` / metrics, model/model.py:300-360): mean squared and mean
+        absolute error over all target components; ``batches`` yields (graph batch, target, atom selector | None)."""
+        self.model.eval()
+        se = torch.zeros((), dtype=torch.float64, device=self.opt.flat_p.device)
+        ae = torch.zeros_like(se)
+        n = 0
+        for batch, target, sel in batches:
+            out = self.model(batch)
+            if isinstance(out, dict):
+                out = out[self.output_key or next(iter(out))]
+            if sel is not None:
+                out = out[sel]
+            d = (out - target).double()
+            se += (d * d).sum()
+            ae += d.abs().sum()
+            n += d.numel()
+        if self.world > 1:
+            t = torch.stack([se, ae, torch.tensor(float(n), dtype=torch.float64, device=se.device)])
+            torch.distributed.all_reduce(t, group=self.pg)
+            se, ae, n = t[0], t[1], float(t[2])
+        n = max(float(n), 1.0)
+        return {"mse": float(se) / n, "mae": float(ae) / n}

@@ -16,6 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from matten_b200.dataset import TensorDataset  # noqa: E402
 from matten_b200.model_factory import AtomicTensorModel, ScalarTensorModel  # noqa: E402
 from matten_b200.predict import save_checkpoint  # noqa: E402
+from matten_b200.schedule import EarlyStopping, ReduceLROnPlateau  # noqa: E402
 from matten_b200.train import Trainer  # noqa: E402
 
 
@@ -28,6 +29,7 @@ def main():
     ap.add_argument("--lr", type=float, default=0.01)
     ap.add_argument("--weight-decay", type=float, default=1e-5)
     ap.add_argument("--out", default=None, help="write model_final.ckpt here")
+    ap.add_argument("--val", default=None, help="validation file: enables ReduceLROnPlateau and early stopping on its MAE")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -58,14 +60,29 @@ def main():
     torch.manual_seed(3)
     model = cls(hp, {"allowed_species": ds.species}, task_name=key).to(dev)
     trainer = Trainer(model, lr=args.lr, weight_decay=args.weight_decay, output_key=key)
+    val = None
+    if args.val:
+        kw = dict(atom_selector="atom_selector") if args.atomic else {}
+        val = TensorDataset(args.val, 5.0, key, "irreps", hp["output_formula"], device=dev, **kw)
+    sched = ReduceLROnPlateau(trainer.opt, mode="min", factor=0.5, patience=50)  # config_final.yaml:17-23
+    stopper = EarlyStopping(mode="min", patience=150)                            # materials_tensor.yaml:86-92
     for epoch in range(args.epochs):
         tot, n = 0.0, 0
         for batch, target, sel in ds.batches(args.batch_size, dev, shuffle=True, seed=epoch, rank=rank, world=world):
             loss = trainer.step(batch, target, atom_selector=sel)
             tot += float(loss)
             n += 1
+        msg = f"epoch {epoch}: mean training loss {tot / max(n, 1):.6f} over {n} steps"
+        if val is not None:
+            m = trainer.evaluate(val.batches(args.batch_size, dev, rank=rank, world=world))
+            sched.step(m["mae"])
+            msg += f", val MAE {m['mae']:.6f}, lr {trainer.opt.lr:g}"
+            if stopper.step(m["mae"]):
+                if rank == 0:
+                    print(msg + " -- early stop", flush=True)
+                break
         if rank == 0:
-            print(f"epoch {epoch}: mean training loss {tot / max(n, 1):.6f} over {n} steps", flush=True)
+            print(msg, flush=True)
     if args.out and rank == 0:
         os.makedirs(args.out, exist_ok=True)
         save_checkpoint(model.eval(), os.path.join(args.out, "model_final.ckpt"))
