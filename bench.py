@@ -356,7 +356,8 @@ def run_ours(args):
         layers.append({"x_dim": key[0], "out_dim": key[2], "weight_numel": key[3], "ms": round(ms, 4),
                        "algorithmic_MB": round(nbytes / 1e6, 2), "GBps": round(nbytes / ms / 1e6, 1)})
     achieved = conv_bytes / conv_ms / 1e6 if conv_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "mt::conv_fwd_kernel (4 launches per step, one per PointConv layer)",
+    roofline = {"bound": "hbm", "kernel": "mt_conv_fwd = mt::edge_prepare_kernel + mt::conv_fwd_tc_kernel<NE> (4 calls per step, one per "
+                          "PointConv layer; CUDA events around each call on the launching stream)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": None, "peak_source": peak_src, "conv_ms_per_step": round(conv_ms, 4),
                 "conv_share_of_step": round(conv_ms / ms_res, 3), "layers": layers}
