@@ -184,3 +184,32 @@ def test_full_size_properties():
     assert torch.isfinite(out_big).all()
     # every tile of 8 crystals is a copy of the small batch: identical results, bit for bit
     assert torch.equal(out_big.reshape(64, 8, 6), out_small.unsqueeze(0).expand(64, 8, 6))
+
+
+def test_cuda_graph_replay_is_bitwise_equal_and_keeps_the_error_word():
+    """``CapturedForward`` (what bench.py times): the replayed graph gives bit-identical predictions to the
+    kernel-by-kernel forward, new inputs of the same shape flow through the static buffers, and the device error word
+    (bad species) is still raised."""
+    from matten_b200.data.synthetic import synthetic_batch
+    from matten_b200.graphs import CapturedForward
+
+    dev = torch.device("cuda:0")
+    _, prod = build_pair(HP_LMAX2, SPECIES8, torch.float32, dev, seed=5)
+    b1 = _dev_batch(synthetic_batch(4, seed=0), dev, torch.float32)
+    b2 = _dev_batch(synthetic_batch(4, seed=1), dev, torch.float32)
+    with torch.no_grad():
+        want1 = prod(dict(b1))["elastic_tensor_full"].clone()
+        want2 = prod(dict(b2))["elastic_tensor_full"].clone()
+        cf = CapturedForward(prod)
+        got1 = cf(b1)["elastic_tensor_full"].clone()
+        got2 = cf(b2)["elastic_tensor_full"].clone()
+        got1b = cf(b1, slot=1)["elastic_tensor_full"].clone()
+    assert torch.equal(got1, want1) and torch.equal(got2, want2) and torch.equal(got1b, want1)
+    assert not torch.equal(want1, want2)
+    bad = dict(b1)
+    bad["atomic_numbers"] = b1["atomic_numbers"].clone()
+    bad["atomic_numbers"][0] = 99
+    with pytest.raises(RuntimeError, match="Invalid atomic numbers"):
+        cf(bad)
+    with torch.no_grad():
+        assert torch.equal(cf(b1)["elastic_tensor_full"], want1)  # the flag is cleared by the next replay
