@@ -21,7 +21,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import torch

@@ -9,7 +9,7 @@ pymatgen needed: the records are parsed directly.  Targets are converted to irre
 from __future__ import annotations
 
 import json
-from typing import Any, Dict, List, Optional, Sequence
+from typing import Any, Dict, List, Optional
 
 import numpy as np
 import torch

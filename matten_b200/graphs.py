@@ -9,7 +9,7 @@ graph holds exactly the kernels the eager path launches.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Dict, Tuple
 
 import torch
 

@@ -17,7 +17,7 @@ import functools
 import itertools
 import math
 from fractions import Fraction
-from typing import Iterable, List, Sequence, Tuple, Union
+from typing import List, Tuple, Union
 
 import torch
 

@@ -9,7 +9,7 @@ returns MT_EARCH which is raised as RuntimeError.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence
 
 import torch
 

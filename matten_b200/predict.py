@@ -14,7 +14,6 @@ for ``is_atomic_tensor``) follows the reference.
 """
 from __future__ import annotations
 
-import io
 import os
 import pickle
 import warnings

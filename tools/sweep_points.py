@@ -1,5 +1,6 @@
 """A few points of the conv sweep (A/B experiments): python tools/sweep_points.py lmax,mul,E [...]"""
-import json, os, sys, subprocess
+import os
+import sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from matten_b200 import o3, ops
