@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MT_ABI_VERSION 1
+#define MT_ABI_VERSION 2
 #define MT_MAX_MLP_LAYERS 6
 #define MT_LMAX 4
 
@@ -177,6 +177,31 @@ int mt_species_embed(int dtype, const int64_t* atomic_numbers, int z_given, cons
  * mlp: num_layers weight matrices, weights[i] is [sizes[i], sizes[i+1]] row-major (the
  * e3nn FullyConnectedNet layout), applied as act(x @ W / sqrt(sizes[i])) * act_cst on
  * all but the last layer; sizes[num_layers] == weight_numel of the tensor product. */
+#define MT_TC_MAX_PARTS 4
+#define MT_TC_MAX_BI 64
+/* One part of the tcgen05 plan (device tables, int32):
+ *   row_wcol [num_tiles*128] : weight column held by every A row / TMEM lane (-1 = zero row)
+ *   bi_hdr   [num_bi,8]      : {bundle id (csrc/generated/cg_bundles.cuh), mode (0 = lane per channel, 1 = 16x256b
+ *                              edge phases), channels per row block, active-path mask, quarter, slot of path 0 / 1 / 2
+ *                              (2 * tile + half)}
+ *   bi_lane  [num_bi,32,4]   : per lane {offset of x[u,:] inside the part's window, out offset of path 0 / 1 / 2
+ *                              (-1 = this lane stores nothing for the path)}
+ *   q_list   [4,MT_TC_MAX_BI], q_count[4]: bundle instances of every quarter (32 TMEM lanes = one warp
+ *                              scheduler), heaviest first */
+typedef struct {
+  int32_t num_tiles;
+  int32_t a_rows;       /* A rows kept in shared memory: a multiple of 32 above the last used row */
+  int32_t num_bi;
+  int32_t x_lo, x_cols; /* window of the x row this part gathers (floats; multiples of 4 / 8) */
+  int32_t lmax;         /* largest degree among its bundles (selects the kernel instantiation) */
+  int32_t cost;         /* relative cost: share of the CTAs */
+  int32_t q_count[4];
+  const int32_t* row_wcol; /* device */
+  const int32_t* bi_hdr;   /* device */
+  const int32_t* bi_lane;  /* device */
+  const int32_t* q_list;   /* device */
+} mt_conv_tc_part;
+
 typedef struct {
   int32_t x_dim;        /* row length of x (node features)          */
   int32_t y_dim;        /* row length of sh (edge attrs)            */
@@ -188,22 +213,14 @@ typedef struct {
   int32_t mlp_sizes[MT_MAX_MLP_LAYERS + 1];
   int32_t mlp_act;      /* mt_act of the hidden layers              */
   double mlp_act_cst;   /* normalize2mom constant of that activation */
-  /* Optional tables of the tcgen05 path (fp32, last hidden size <= 32, <= 512 TMEM rows); tc_num_tiles
-   * == 0 disables it.  The weight columns are laid out as rows of the MMA A operand in groups of 32
-   * TMEM lanes ("quarters" of a 128-row tile), one (l1,l2,l3) type per group or several small types
-   * packed into one group as lane-phased sub-items:
-   *   tc_row_wcol [tc_num_tiles*128]   : weight column of every A row (-1 = zero row)
-   *   tc_sub_hdr  [tc_num_sub,8]       : {cg_type_id, cols_per_warp, first TMEM lane in the quarter,
-   *                                       tile, quarter, 2*l3+1, 0, 0}  (l1,l2,l3 <= 2 only)
-   *   tc_sub_slot [tc_num_sub,32,4]    : per lane {x offset, sh offset, out offset, valid}
-   *   tc_q_list   [4,64], tc_q_count[4]: sub-items of every quarter, heaviest first            */
-  int32_t tc_num_tiles;
-  int32_t tc_num_sub;
-  const int32_t* tc_row_wcol; /* device */
-  const int32_t* tc_sub_hdr;  /* device */
-  const int32_t* tc_sub_slot; /* device */
-  const int32_t* tc_q_list;   /* device */
-  int32_t tc_q_count[4];
+  /* Optional tables of the tcgen05 path (fp32, MLP layer sizes <= 32, <= 2 hidden layers); tc_num_parts == 0
+   * disables it.  Built by matten_b200/tcplan.py (vocabulary there): the weight columns are rows of the MMA A
+   * operand = lanes of tensor memory; a *bundle instance* is a group of input channels x a compile-time list
+   * of (l2, l3) paths sharing the loads of x[u, :] and of the edge's spherical harmonics; a *part* owns <= 4
+   * tiles of 128 rows and a window of the x row (layers whose weights exceed 512 rows are cut into parts). */
+  int32_t tc_num_parts;
+  int32_t tc_y_lmax;    /* edge attrs are the harmonics 0 .. tc_y_lmax, one block each, in order */
+  mt_conv_tc_part tc_parts[MT_TC_MAX_PARTS];
   /* Tables of the backward pass (mt_conv_bwd), organised by INPUT channel so that the gradient of a
    * gathered x row is a register sum in fixed path order; bw_num_items == 0: forward-only plan.
    *   bw_item_hdr [bw_num_items,4]   : {l1, cols_per_warp, first path, path count}
@@ -222,15 +239,22 @@ typedef struct {
  *   (sum_{e: dst(e)=n} msg_e) / sqrt(avg_num_neighbors)        if num_neigh == NULL
  *   (sum ...)             / sqrt(num_neigh[n])                  otherwise (reference
  *   src/matten/nn/conv.py:116-120). Summation order is the CSR order: deterministic. */
-/* workspace (bytes) of the tcgen05 path: the hidden activations of the radial MLP as bf16 hi/mid/lo
- * planes (192 B per edge) and 16-byte padded sh rows, both in receiver-sorted order.  0 when the plan /
- * dtype runs on the FMA-pipe kernel, which needs none. */
+/* workspace (bytes): 0 for every current kernel (the tcgen05 path evaluates the hidden layers of the radial MLP
+ * inside the fused kernel); kept in the ABI so that a caller never has to change when a kernel needs scratch. */
 size_t mt_conv_fwd_workspace_bytes(const mt_conv_plan* plan, int dtype, int64_t N, int64_t E);
 int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* sh,
                 const void* emb, const void* const* mlp_weights, const int32_t* rowptr,
                 const int32_t* perm, const int32_t* src_sorted, double avg_num_neighbors,
                 const void* num_neigh, void* out, void* workspace, size_t workspace_bytes, int64_t N,
                 int64_t E, mt_stream stream);
+
+/* Which fp32 kernel mt_conv_fwd uses: 0 = automatic (tcgen05 when the plan qualifies, else FMA pipes), 1 = tcgen05
+ * only (MT_EINVAL when the plan does not qualify), 2 = FMA pipes only.  Process-wide; the initial value comes from
+ * the environment variable MT_CONV_IMPL (auto / tc / fma), read once.  Returns the previous setting. */
+int mt_conv_select_impl(int impl);
+/* Profiling aid: device buffer of >= 32 * 8 int64 that receives the per-warp phase timings (clock64 sums, slot
+ * meanings in csrc/conv_fwd_tc.cuh) of CTA 0 of every following tcgen05 launch; NULL (default) turns it off. */
+void mt_conv_set_debug_buffer(void* device_buffer);
 
 /* Backward of mt_conv_fwd (what autograd does through weight_nn + tp + scatter + div in the reference,
  * src/matten/nn/conv.py:111-120).  Inputs as in mt_conv_fwd plus

@@ -4,5 +4,5 @@ hot path of MatTen (wengroup/matten): hand-written CUDA kernels behind a C ABI
 (include/matten_b200.h), bound with ctypes and exposed through modules that mirror the
 reference's ``matten.nn`` / ``matten.model_factory`` API.
 """
-ABI_VERSION = 1
+ABI_VERSION = 2
 __version__ = "0.1.0"

@@ -22,6 +22,19 @@ c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 
 
+MT_TC_MAX_PARTS = 4
+MT_TC_MAX_BI = 64
+
+
+class ConvTcPartStruct(C.Structure):
+    """mt_conv_tc_part"""
+    _fields_ = [
+        ("num_tiles", C.c_int32), ("a_rows", C.c_int32), ("num_bi", C.c_int32), ("x_lo", C.c_int32), ("x_cols", C.c_int32),
+        ("lmax", C.c_int32), ("cost", C.c_int32), ("q_count", C.c_int32 * 4),
+        ("row_wcol", C.c_void_p), ("bi_hdr", C.c_void_p), ("bi_lane", C.c_void_p), ("q_list", C.c_void_p),
+    ]
+
+
 class ConvPlanStruct(C.Structure):
     """mt_conv_plan"""
     _fields_ = [
@@ -29,9 +42,7 @@ class ConvPlanStruct(C.Structure):
         ("item_hdr", C.c_void_p), ("slot_tab", C.c_void_p),
         ("mlp_num_layers", C.c_int32), ("mlp_sizes", C.c_int32 * (MT_MAX_MLP_LAYERS + 1)),
         ("mlp_act", C.c_int32), ("mlp_act_cst", C.c_double),
-        ("tc_num_tiles", C.c_int32), ("tc_num_sub", C.c_int32),
-        ("tc_row_wcol", C.c_void_p), ("tc_sub_hdr", C.c_void_p), ("tc_sub_slot", C.c_void_p),
-        ("tc_q_list", C.c_void_p), ("tc_q_count", C.c_int32 * 4),
+        ("tc_num_parts", C.c_int32), ("tc_y_lmax", C.c_int32), ("tc_parts", ConvTcPartStruct * MT_TC_MAX_PARTS),
         ("bw_num_items", C.c_int32), ("bw_num_paths", C.c_int32),
         ("bw_item_hdr", C.c_void_p), ("bw_lane_tab", C.c_void_p), ("bw_path_tab", C.c_void_p),
     ]
@@ -67,6 +78,8 @@ SIGNATURES = {
     "mt_conv_fwd_workspace_bytes": (_Z, [C.POINTER(ConvPlanStruct), _I, _L, _L]),
     "mt_conv_fwd": (_I, [C.POINTER(ConvPlanStruct), _I, _V, _V, _V, C.POINTER(_V), _V, _V, _V, _D, _V, _V,
                          _V, _Z, _L, _L, _V]),
+    "mt_conv_select_impl": (_I, [_I]),
+    "mt_conv_set_debug_buffer": (None, [_V]),
     "mt_conv_bwd_workspace_bytes": (_Z, [C.POINTER(ConvPlanStruct), _I, _L, _L]),
     "mt_conv_bwd": (_I, [C.POINTER(ConvPlanStruct), _I, _V, _V, _V, C.POINTER(_V), _V, _V, _V, _V, _V, _D, _V, _V, _V,
                          C.POINTER(_V), _V, _Z, _L, _L, _V]),

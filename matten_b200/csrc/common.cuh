@@ -80,6 +80,7 @@ struct f2 {
   __device__ __forceinline__ explicit f2(double a) : v(make_float2((float)a, (float)a)) {}
   __device__ __forceinline__ explicit f2(int a) : v(make_float2((float)a, (float)a)) {}
 };
+__device__ __forceinline__ f2 operator-(f2 a) { return f2(-a.v.x, -a.v.y); }  // folds into an operand modifier
 __device__ __forceinline__ f2 operator*(f2 a, f2 b) {
   f2 r;
   r.v = __fmul2_rn(a.v, b.v);

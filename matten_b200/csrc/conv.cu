@@ -19,11 +19,30 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
                     const int32_t* src_sorted, double avg, const void* num_neigh, void* out, void* workspace,
                     size_t workspace_bytes, int64_t N, int64_t E, cudaStream_t st, int* used);
 size_t conv_fwd_tc_workspace_bytes(const mt_conv_plan* plan, int64_t E);
+void conv_fwd_tc_set_debug(void* p);
 
-static int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return (s && *s) ? atoi(s) : dflt;
+// Tuning overrides (MT_CONV_*) are read from the environment ONCE per process: nothing on the call path touches getenv.
+struct ConvEnv {
+  int smem_kb, ec, tn, threads, ctas_per_sm, impl;
+  ConvEnv() {
+    auto geti = [](const char* name) {
+      const char* s = getenv(name);
+      return (s && *s) ? atoi(s) : -1;
+    };
+    smem_kb = geti("MT_CONV_SMEM_KB");
+    ec = geti("MT_CONV_EC");
+    tn = geti("MT_CONV_TN");
+    threads = geti("MT_CONV_THREADS");
+    ctas_per_sm = geti("MT_CONV_CTAS_PER_SM");
+    const char* s = getenv("MT_CONV_IMPL");
+    impl = (s && strcmp(s, "tc") == 0) ? 1 : ((s && strcmp(s, "fma") == 0) ? 2 : 0);
+  }
+};
+static ConvEnv& conv_env() {
+  static ConvEnv e;
+  return e;
 }
+static int env_or(int v, int dflt) { return v >= 0 ? v : dflt; }
 
 static int pad_hp(int h) {
   if (h <= 8) return 8;
@@ -81,18 +100,18 @@ static int conv_fwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
 
   // chunk size from the shared-memory budget
   const size_t per_edge = (size_t)(2 * hp_max + p.xs_stride + p.y_dim) * sizeof(T);
-  size_t budget = (size_t)env_int("MT_CONV_SMEM_KB", sizeof(T) == 4 ? 64 : 96) * 1024;
+  size_t budget = (size_t)env_or(conv_env().smem_kb, sizeof(T) == 4 ? 64 : 96) * 1024;
   int EC = (int)(budget / per_edge);
   EC = EC / 8 * 8;
   if (EC > 256) EC = 256;
   if (EC < 8) EC = 8;
-  EC = env_int("MT_CONV_EC", EC);
+  EC = env_or(conv_env().ec, EC);
   p.chunk_edges = EC;
   double avg_deg = N > 0 ? (double)E / (double)N : 1.0;
   int TN = (int)((double)EC / (avg_deg > 1.0 ? avg_deg : 1.0));
   if (TN < 1) TN = 1;
   if (TN > 32) TN = 32;
-  p.tile_nodes = env_int("MT_CONV_TN", TN);
+  p.tile_nodes = env_or(conv_env().tn, TN);
   size_t hidden_w = 0;
   for (int i = 0; i + 1 < p.nl; ++i) hidden_w += (size_t)p.sizes[i] * p.sizes[i + 1];
   const size_t smem = (size_t)EC * per_edge + hidden_w * sizeof(T);
@@ -102,7 +121,7 @@ static int conv_fwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
   // (CTAs/SM x threads) = (3 x 256) / (2 x 256) / (2 x 128): sh lmax 2: 4.6 / 5.5 / 8.7; lmax 3: 16.3 / 15.2 / 25.7;
   // lmax 4: 45.0 / 36.5 / 17.0.
   const int sh_lmax = p.y_dim >= 25 ? 4 : (p.y_dim >= 16 ? 3 : 2);
-  const int threads = env_int("MT_CONV_THREADS", (sizeof(T) == 4 && sh_lmax >= 4) ? 128 : 256);
+  const int threads = env_or(conv_env().threads, (sizeof(T) == 4 && sh_lmax >= 4) ? 128 : 256);
   MT_REQUIRE(threads >= 32 && threads <= 256 && threads % 32 == 0, "MT_CONV_THREADS must be 32..256");
   int64_t tiles = ceil_div<int64_t>(N, p.tile_nodes);
   int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -110,7 +129,7 @@ static int conv_fwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
   const int reg_limit = sizeof(T) == 4 ? (HP <= 32 ? 3 : 2) : 1;  // conv_fwd_min_blocks<T, HP>()
   if (ctas_per_sm > reg_limit) ctas_per_sm = reg_limit;
   if (sizeof(T) == 4 && sh_lmax >= 3 && ctas_per_sm > 2) ctas_per_sm = 2;
-  ctas_per_sm = env_int("MT_CONV_CTAS_PER_SM", ctas_per_sm);
+  ctas_per_sm = env_or(conv_env().ctas_per_sm, ctas_per_sm);
   int64_t grid = (int64_t)kNumSMs * ctas_per_sm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
@@ -128,6 +147,14 @@ static int conv_fwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
 using namespace mt;
 
 extern "C" {
+
+void mt_conv_set_debug_buffer(void* device_buffer) { conv_fwd_tc_set_debug(device_buffer); }
+
+int mt_conv_select_impl(int impl) {
+  const int old = conv_env().impl;
+  if (impl >= 0 && impl <= 2) conv_env().impl = impl;
+  return old;
+}
 
 size_t mt_conv_fwd_workspace_bytes(const mt_conv_plan* plan, int dtype, int64_t N, int64_t E) {
   (void)N;
@@ -149,17 +176,17 @@ int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* 
   MT_REQUIRE(num_neigh != nullptr || avg_num_neighbors > 0.0, "avg_num_neighbors must be > 0");
   for (int i = 0; i < plan->mlp_num_layers; ++i) MT_REQUIRE(mlp_weights[i] != nullptr, "null MLP weight %d", i);
   // fp32: Blackwell tensor-core path (radial MLP on tcgen05, weights in TMEM) when the plan qualifies;
-  // MT_CONV_IMPL=fma forces the FMA-pipe kernel (used by the tests to cross-check the two)
+  // mt_conv_select_impl(2) forces the FMA-pipe kernel (used by the tests to cross-check the two)
   if (dtype == MT_F32) {
-    const char* impl = getenv("MT_CONV_IMPL");
-    if (!(impl && strcmp(impl, "fma") == 0)) {
+    const int impl = conv_env().impl;
+    if (impl != 2) {
       int used = 0;
       rc = conv_fwd_tc_try(plan, x, sh, emb, mlp_weights, rowptr, perm, src_sorted, avg_num_neighbors, num_neigh,
                            out, workspace, workspace_bytes, N, E, as_stream(stream), &used);
       if (rc != MT_OK) return rc;
       if (used) return MT_OK;
-      if (impl && strcmp(impl, "tc") == 0)
-        return set_error(MT_EINVAL, "MT_CONV_IMPL=tc but this plan/shape does not qualify for the tcgen05 path");
+      if (impl == 1)
+        return set_error(MT_EINVAL, "tcgen05 path requested but this plan/shape does not qualify for it");
     }
   }
   MT_DISPATCH_DTYPE(dtype, {

@@ -5,33 +5,64 @@
 
 namespace mt {
 
-static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+constexpr size_t kTcSmemLimit = (size_t)227 * 1024 - 1024;  // dynamic + static shared memory must fit 227 KB
 
-// widest chunk (MMA N) whose staging buffers fit the shared memory; 0: none
-static int tc_pick_ne(const mt_conv_plan* plan) {
-  const int y_pad = (plan->y_dim + 3) & ~3;
-  for (int ne = tc_chunk_cols(plan->tc_num_tiles); ne >= 64; ne >>= 1) {
-    const TcSmemLayout L = tc_smem_layout(plan->tc_num_tiles, plan->x_dim, y_pad, plan->tc_num_sub, ne);
-    if (L.total + 512 <= (size_t)227 * 1024) return ne;  // dynamic + static shared memory must fit 227 KB
+// widest chunk (MMA N, a multiple of 16) whose staging buffers fit the shared memory; 0: none
+static int tc_w_rows(const mt_conv_plan* plan) {
+  const int nh = plan->mlp_num_layers - 1;
+  return (nh > 0 ? tc_pad8(plan->mlp_sizes[0]) : 0) + (nh > 1 ? tc_pad8(plan->mlp_sizes[1]) : 0);
+}
+
+static int tc_pick_ne(const mt_conv_tc_part& part, int y_lmax, int w_rows) {
+  static const int cand[] = {256, 128, 80, 64, 48, 32};
+  const int y_pad = sh_pad_len(y_lmax);
+  for (int ne : cand) {
+    if (2 * part.num_tiles * ne > 512) continue;
+    const TcSmemLayout L = tc_smem_layout(part.a_rows, part.x_cols, y_pad, part.num_bi, ne, w_rows);
+    if (L.total <= kTcSmemLimit) return ne;
   }
   return 0;
 }
 
 static bool tc_plan_qualifies(const mt_conv_plan* plan) {
-  if (plan->tc_num_tiles <= 0 || plan->tc_num_tiles > kTcMaxTiles) return false;
-  if (plan->tc_num_sub <= 0 || plan->tc_num_sub > kTcMaxSub) return false;
-  if (!plan->tc_row_wcol || !plan->tc_sub_hdr || !plan->tc_sub_slot || !plan->tc_q_list) return false;
-  if (plan->mlp_num_layers > 3) return false;  // at most two hidden layers in the preparation kernel
+  if (plan->tc_num_parts <= 0 || plan->tc_num_parts > MT_TC_MAX_PARTS) return false;
+  if (plan->tc_y_lmax < 0 || plan->tc_y_lmax > MT_LMAX) return false;
+  if (plan->mlp_num_layers > 3) return false;  // at most two hidden layers are kept in registers
   for (int i = 0; i < plan->mlp_num_layers; ++i)
     if (plan->mlp_sizes[i] > kTcK) return false;
-  if (plan->x_dim > 65535 || plan->y_dim > 252 || (plan->x_dim & 3) != 0) return false;  // 16-byte bulk copies
-  return tc_pick_ne(plan) > 0;
+  if ((plan->x_dim & 3) != 0) return false;  // TMA: rows must be multiples of 16 bytes
+  for (int i = 0; i < plan->tc_num_parts; ++i) {
+    const mt_conv_tc_part& pt = plan->tc_parts[i];
+    if (pt.num_tiles <= 0 || pt.num_tiles > kTcMaxTiles || pt.num_bi <= 0 || pt.num_bi > kTcMaxBI) return false;
+    if (pt.a_rows <= 0 || pt.a_rows > pt.num_tiles * 128 || (pt.a_rows & 31) != 0) return false;
+    if (!pt.row_wcol || !pt.bi_hdr || !pt.bi_lane || !pt.q_list) return false;
+    if (pt.x_cols <= 0 || pt.x_cols > 256 || (pt.x_cols & 7) != 0 || (pt.x_lo & 3) != 0) return false;
+    if (tc_pick_ne(pt, plan->tc_y_lmax, tc_w_rows(plan)) == 0) return false;
+  }
+  return true;
 }
 
-size_t conv_fwd_tc_workspace_bytes(const mt_conv_plan* plan, int64_t E) {
-  if (!tc_plan_qualifies(plan) || E <= 0) return 0;
-  const int y_pad = (plan->y_dim + 3) & ~3;
-  return align256((size_t)E * 192) + align256((size_t)E * y_pad * 4) + 256;
+size_t conv_fwd_tc_workspace_bytes(const mt_conv_plan*, int64_t) { return 0; }
+
+static long long* g_tc_dbg = nullptr;  // phase-timing buffer of the next launches (mt_conv_set_debug_buffer)
+void conv_fwd_tc_set_debug(void* p) { g_tc_dbg = static_cast<long long*>(p); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    tried = true;
+  }
+  return fn;
 }
 
 // returns MT_OK and sets *used = 1 when the tensor-core path ran; *used = 0 when the plan/shape does not
@@ -40,29 +71,25 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
                     const void* const* mlp_weights, const int32_t* rowptr, const int32_t* perm,
                     const int32_t* src_sorted, double avg, const void* num_neigh, void* out, void* workspace,
                     size_t workspace_bytes, int64_t N, int64_t E, cudaStream_t st, int* used) {
+  (void)workspace;
+  (void)workspace_bytes;
   *used = 0;
   if (!tc_plan_qualifies(plan)) return MT_OK;
   if (E >= (int64_t)2147483647 || N >= (int64_t)2147483647) return MT_OK;
-  const size_t need = conv_fwd_tc_workspace_bytes(plan, E);
-  if (E > 0 && (workspace == nullptr || workspace_bytes < need)) return MT_OK;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return MT_OK;
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (encode == nullptr) return set_error(MT_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   p.x_dim = plan->x_dim;
   p.y_dim = plan->y_dim;
+  p.y_lmax = plan->tc_y_lmax;
   p.out_dim = plan->out_dim;
-  p.num_tiles = plan->tc_num_tiles;
-  p.num_sub = plan->tc_num_sub;
-  p.row_wcol = plan->tc_row_wcol;
-  p.sub_hdr = plan->tc_sub_hdr;
-  p.sub_slot = plan->tc_sub_slot;
-  p.q_list = plan->tc_q_list;
-  for (int q = 0; q < 4; ++q) p.q_count[q] = plan->tc_q_count[q];
   p.nl = plan->mlp_num_layers;
   for (int i = 0; i <= p.nl; ++i) p.sizes[i] = plan->mlp_sizes[i];
   for (int i = 0; i < p.nl; ++i) p.w[i] = static_cast<const float*>(mlp_weights[i]);
   p.act = plan->mlp_act;
   p.act_cst = (float)plan->mlp_act_cst;
-  p.x = static_cast<const float*>(x);
   p.sh = static_cast<const float*>(sh);
   p.emb = static_cast<const float*>(emb);
   p.rowptr = rowptr;
@@ -73,41 +100,67 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
   p.out = static_cast<float*>(out);
   p.N = N;
   p.E = E;
-  p.y_pad = (p.y_dim + 3) & ~3;
-  {
-    // workspace: 256-byte aligned sub-buffers
-    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
-    p.hplanes = reinterpret_cast<__nv_bfloat16*>(base);
-    p.ysorted = reinterpret_cast<float*>(base + align256((size_t)E * 192));
-  }
-  const char* dbg = getenv("MT_CONV_TC_DEBUG");
-  p.dbg = (dbg && *dbg) ? reinterpret_cast<long long*>(strtoull(dbg, nullptr, 10)) : nullptr;
-  const int NE = tc_pick_ne(plan);
-  const TcSmemLayout L = tc_smem_layout(p.num_tiles, p.x_dim, p.y_pad, p.num_sub, NE);
-  if (E > 0) {
-    int64_t g = ceil_div<int64_t>(E, kPrepThreads);
-    const int64_t cap = (int64_t)kNumSMs * 16;
-    if (g > cap) g = cap;
-    edge_prepare_kernel<<<(unsigned)g, kPrepThreads, 0, st>>>(p);
-    MT_LAUNCH_OK();
-  }
+  p.num_parts = plan->tc_num_parts;
+  p.dbg = g_tc_dbg;
+  // CTAs per part follow the part's cost (every part walks all edges; heavy parts get more SMs)
   int64_t grid = kNumSMs;
-  if (grid > N) grid = N;
-  if (grid < 1) grid = 1;
-  static thread_local size_t configured[3] = {0, 0, 0};
-  const int vi = NE == 256 ? 0 : (NE == 128 ? 1 : 2);
-  if (L.total > configured[vi]) {
-    if (NE == 256)
-      MT_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    else if (NE == 128)
-      MT_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    else
-      MT_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    configured[vi] = L.total;
+  if (grid > N * p.num_parts) grid = N * p.num_parts;
+  if (grid < p.num_parts) grid = p.num_parts;
+  double cost_sum = 0;
+  for (int i = 0; i < p.num_parts; ++i) cost_sum += plan->tc_parts[i].cost > 0 ? plan->tc_parts[i].cost : 1;
+  int assigned = 0;
+  int lmax = 0;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  size_t smem_max = 0;
+  for (int i = 0; i < p.num_parts; ++i) {
+    const mt_conv_tc_part& pt = plan->tc_parts[i];
+    TcPartParams& q = p.part[i];
+    q.num_tiles = pt.num_tiles;
+    q.a_rows = pt.a_rows;
+    q.num_bi = pt.num_bi;
+    q.x_lo = pt.x_lo;
+    q.x_cols = pt.x_cols;
+    q.ne = tc_pick_ne(pt, plan->tc_y_lmax, tc_w_rows(plan));
+    for (int k = 0; k < 4; ++k) q.q_count[k] = pt.q_count[k];
+    q.row_wcol = pt.row_wcol;
+    q.bi_hdr = pt.bi_hdr;
+    q.bi_lane = pt.bi_lane;
+    q.q_list = pt.q_list;
+    const double c = pt.cost > 0 ? pt.cost : 1;
+    int n = (i + 1 == p.num_parts) ? (int)grid - assigned : (int)((double)grid * c / cost_sum + 0.5);
+    const int left = p.num_parts - 1 - i;
+    if (n > (int)grid - assigned - left) n = (int)grid - assigned - left;
+    if (n < 1) n = 1;
+    if (n > N && N > 0) n = (int)N;
+    q.cta_first = assigned;
+    q.cta_count = n;
+    assigned += n;
+    if (pt.lmax > lmax) lmax = pt.lmax;
+    const TcSmemLayout L = tc_smem_layout(q.a_rows, q.x_cols, sh_pad_len(p.y_lmax), q.num_bi, q.ne, tc_w_rows(plan));
+    if (L.total > smem_max) smem_max = L.total;
+    // x as a 2D tensor [N][x_dim] of fp32, box {x_cols, 1}: tile::gather4 fetches 4 arbitrary rows per instruction
+    cuuint64_t dims[2] = {(cuuint64_t)plan->x_dim, (cuuint64_t)(N > 0 ? N : 1)};
+    cuuint64_t strides[1] = {(cuuint64_t)plan->x_dim * 4};
+    cuuint32_t box[2] = {(cuuint32_t)q.x_cols, 1};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(x), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(MT_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   }
-  if (NE == 256) conv_fwd_tc_kernel<256><<<(unsigned)grid, tc_threads(256), L.total, st>>>(p);
-  else if (NE == 128) conv_fwd_tc_kernel<128><<<(unsigned)grid, tc_threads(128), L.total, st>>>(p);
-  else conv_fwd_tc_kernel<64><<<(unsigned)grid, tc_threads(64), L.total, st>>>(p);
+  grid = assigned;
+  static thread_local size_t configured[2] = {0, 0};
+  const int vi = lmax <= 2 ? 0 : 1;
+  if (smem_max > configured[vi]) {
+    if (vi == 0)
+      MT_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemLimit));
+    else
+      MT_CUDA_OK(cudaFuncSetAttribute(conv_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemLimit));
+    configured[vi] = kTcSmemLimit;
+  }
+  if (vi == 0) conv_fwd_tc_kernel<2><<<(unsigned)grid, kTcThreads, smem_max, st>>>(p, maps);
+  else conv_fwd_tc_kernel<4><<<(unsigned)grid, kTcThreads, smem_max, st>>>(p, maps);
   MT_LAUNCH_OK();
   *used = 1;
   return MT_OK;

@@ -1,84 +1,84 @@
-// Fused convolution forward, Blackwell-native version (fp32 storage, l <= 2 tensor-product types):
+// Fused convolution forward, Blackwell-native version (fp32 storage):
 //
-//   last radial-MLP layer  w[e, c] = sum_k h[e,k] W[k,c]   ->  tcgen05.mma (bf16 x3 split, fp32 accumulate)
-//   accumulators                                           ->  TMEM  (row = weight column c, column = edge e)
-//   uvu Clebsch-Gordan contraction + per-receiver sum      ->  FP32 FMA pipes, operands in shared memory,
-//                                                              per-node sums in registers (CSR order, no atomics)
+//   hidden layers of the radial MLP  h = act(act(emb W1) W2)      -> FP32 FMA pipes, dedicated warps, lane == edge
+//   last radial-MLP layer            w[e, c] = sum_k h[e,k] W[k,c] -> tcgen05.mma (bf16 x3 split, fp32 accumulate)
+//   accumulators                                                   -> TMEM  (lane = weight column c, column = edge e)
+//   gathered sender rows x[src]                                    -> TMA tile::gather4 (4 rows per instruction)
+//   uvu Clebsch-Gordan contraction + per-receiver sum              -> FP32 FMA pipes (FFMA2: two edges per instruction),
+//                                                                     operands in shared memory, per-node sums in
+//                                                                     registers (CSR order, no atomics)
 //
-// Same contract as conv_fwd.cuh (reference src/matten/nn/utils.py:260-263 + src/matten/nn/conv.py:113-120):
-// the per-edge tensor-product weights [E, weight_numel] and the messages [E, D_mid] never leave the SM.
+// Same contract as conv_fwd.cuh (reference src/matten/nn/utils.py:260-263 + src/matten/nn/conv.py:113-120): neither
+// the hidden activations, nor the per-edge tensor-product weights [E, weight_numel], nor the messages [E, D_mid]
+// ever leave the SM.  One launch per call, no workspace.
 //
-// Two kernels:
-//  (1) edge_prepare_kernel: one thread per receiver-sorted edge evaluates the small hidden layers of the radial MLP
-//      (e.g. 8 -> 32 -> 32) and stores h as three bf16 planes (hi/mid/lo) in the K-major core-matrix layout the
-//      MMA wants, plus the edge's spherical-harmonic row padded to 16 bytes.  192 + 48 bytes per edge.
-//  (2) conv_fwd_tc_kernel: 1 CTA per SM, persistent over a contiguous node range (balanced by edge count),
-//      warp specialised:
-//        warp 0      builds node-aligned chunks (every node's edges padded to a multiple of 4 columns, <= 64
-//                    columns) and issues cp.async.bulk copies: gathered sender rows x[src], sh rows, h planes.
-//        warp 1      one thread issues the tcgen05.mma's of the chunk: D[t] (128 x 64, TMEM) = A[t] (128 rows of
-//                    W^T, K = 32) x B^T (64 edges), 6 significant products of the 3 x 3 bf16 split (~2^-24).
-//        warps 4..31 consumers.  Warp w reads TMEM lanes 32*(w%4).. .  A group of 32 TMEM lanes holds 32 weight
-//                    columns of ONE (l1,l2,l3) type (or several small types packed; those run lane-phased).
-//                    Work units (sub-item, node) are handed out dynamically.  Per edge a lane gets w from TMEM
-//                    (tcgen05.ld 32x32b.x4, software pipelined), x / sh from shared memory and runs the generated
-//                    CG contraction; pad columns carry zero weights, so the edge loop has no range checks.
-//      Double buffered TMEM accumulators and x / sh staging; mbarriers: full[b] (bulk-copy bytes + tcgen05.commit),
-//      empty[b] (28 consumer warps), bready / bfree (h planes landed / consumed by the MMAs).
+// One CTA per SM, persistent over a contiguous node range (balanced by edge count), 20 warps = 5 per scheduler:
+//   warps 0..11   consumers.  Warp w reads TMEM lanes 32 (w % 4) .. .  Work units (bundle instance, node) are handed
+//                 out dynamically per quarter.  A bundle instance (matten_b200/tcplan.py) is a group of input channels
+//                 x a compile-time list of paths that share the loads of x[u, :] and Y (generated/cg_bundles.cuh):
+//                   mode L: lane == channel (32 channels), the warp walks the node's edge pairs;
+//                   mode P: 8 / 4 / 2 channels x edge phases through the tcgen05.ld.16x256b fragment
+//                           (thread 4 r + ph: TMEM rows r and r + 8, column pair ph of 4).
+//   warps 12..18  radial MLP.  Blocks of 8 chunk columns are claimed dynamically; four lanes own a column: they load
+//                 the edge's radial embedding and spherical harmonics, evaluate the hidden layers (8 outputs per lane,
+//                 layer inputs exchanged through a shared-memory row), write h as three bf16 planes (the B operand)
+//                 and the harmonics as pair-interleaved rows.  They compute ahead of the buffers: only the stores
+//                 wait for the consumers.
+//   warp 19       control: scheduler (node-aligned chunks: every node's edges padded to a multiple of 4 columns,
+//                 <= NE columns, published up to 3 chunks ahead), TMA gathers of the chunk's sender rows, and the
+//                 chunk's tcgen05.mma's: D[t] (128 x NE, TMEM) = A[t] (128 rows of W^T, K = 32) x B^T (NE edges),
+//                 6 significant products of the 3 x 3 bf16 split (~2^-24).
+//   Single-warp code runs at ~10 cycles per instruction here (every instruction waits for the previous one, nothing
+//   else to issue): the radial MLP therefore needs several warps in flight, and the consumers as many as fit.
+//   Double buffered TMEM accumulators and x / Y staging; mbarriers: go[m] (chunk metadata published), bready[b] (h
+//   planes written), bfree (MMAs have read them), full[b] (gather bytes + Y rows + tcgen05.commit), empty[b]
+//   (consumers done with the stage).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
-#include "generated/cg_gen.cuh"
+#include "generated/cg_bundles.cuh"
 
 namespace mt {
 
-// columns (padded edges) per chunk == MMA N: 2 stages x MT tiles x NE columns must fit the 512 TMEM columns, so
-// small plans take wider chunks (more nodes per chunk: more units to balance, fewer producer round trips)
-__host__ __device__ constexpr int tc_chunk_cols(int MT) { return MT <= 1 ? 256 : (MT == 2 ? 128 : 64); }
 constexpr int kTcK = 32;              // padded size of the last hidden layer == MMA K total
-constexpr int kTcProducerWarps = 4;   // warp 0: chunks + plane / sh copies, warp 1: MMA issue, warps 2-3: x-row copies
-// consumer warps per chunk width (a multiple of 4: warp w reads TMEM quarter w % 4).  Fewer than the 28 that fill a
-// 1024-thread CTA: with 16 (4 per quarter / scheduler) the kernel gets 92 registers per thread and each scheduler's
-// instruction stream stays resident -- measured on the bench layers (ms per call, layers 1..3), 28 warps: 1.19 / 1.40 /
-// 1.47, 24: 1.03 / 1.22 / 1.24, 20: 1.16 / 1.33 / 1.31, 16: 1.09 / 1.11 / 1.18, 12: 1.25 / 1.30 / 1.36.
-__host__ __device__ constexpr int tc_consumer_warps(int NE) { return NE == 128 ? 24 : 16; }
-__host__ __device__ constexpr int tc_threads(int NE) { return 32 * (kTcProducerWarps + tc_consumer_warps(NE)); }
-constexpr int kTcMaxTiles = 4;        // M tiles of 128 rows -> <= 512 weight-column rows
-constexpr int kTcMaxSub = 64;         // sub-items per plan
-constexpr int kTcMaxNodes = 16;       // receiver nodes per chunk
-constexpr int kTcD = 5;               // 2*lmax+1 of the types this kernel handles (l <= 2)
+constexpr int kTcConsumerWarps = 12;  // a multiple of 4: warp w reads TMEM quarter w % 4
+constexpr int kTcMlpWarps = 6;        // radial-MLP warps (+ the TMA gathers of their columns)
+constexpr int kTcFirstMlpWarp = kTcConsumerWarps;
+constexpr int kTcMmaWarp = kTcConsumerWarps + kTcMlpWarps;  // MMA issue
+constexpr int kTcControlWarp = kTcMmaWarp + 1;              // scheduler
+constexpr int kTcThreads = 32 * (kTcControlWarp + 1);       // 20 warps: 5 per scheduler, 96 registers per thread
+constexpr int kTcMaxTiles = 4;        // M tiles of 128 rows per part
+constexpr int kTcMaxBI = 64;          // bundle instances per part
+constexpr int kTcMaxNodes = 32;       // receiver nodes per chunk
+constexpr int kTcMaxParts = 4;
+constexpr int kTcMetaSlots = 4;       // chunk metadata ring: scheduler and MLP warps run ahead of the two stages
 
-// debugging aid: per-warp progress codes of CTA `dbg_block` into a host-visible buffer (MT_CONV_TC_DEBUG)
-// phase timing of CTA 0 (MT_CONV_TC_DEBUG = device pointer to >= 16384 int64): slot layout in tools/tc_debug.py
-// (compiled in only with -DMT_TC_TIMING: the extra code in the consumer loop costs instruction-cache hits)
-#ifdef MT_TC_TIMING
-#define MT_TACC(var) do { if (p.dbg && blockIdx.x == 0) { const long long _n = clock64(); (var) += _n - _tl; _tl = _n; } } while (0)
-#define MT_TIMING_ONLY(...) __VA_ARGS__
-#define MT_DBG(code) do { if (p.dbg && (threadIdx.x & 31) == 0) ((volatile long long*)p.dbg)[256 + blockIdx.x * 32 + (threadIdx.x >> 5)] = (long long)(code); } while (0)
-#define MT_DBG_BLOCK(code) do { if (p.dbg && threadIdx.x == 0) ((volatile long long*)p.dbg)[blockIdx.x] = (long long)(code); } while (0)
-#else
-#define MT_TACC(var) do { } while (0)
-#define MT_TIMING_ONLY(...)
-#define MT_DBG(code) do { } while (0)
-#define MT_DBG_BLOCK(code) do { } while (0)
-#endif
+// columns (padded edges) per chunk == MMA N: 2 stages x MT tiles x NE columns must fit the 512 TMEM columns
+__host__ __device__ constexpr int tc_chunk_cols(int MT) { return MT <= 1 ? 256 : (MT == 2 ? 128 : (MT == 3 ? 80 : 64)); }
+
+struct TcPartParams {
+  int num_tiles;             // MT
+  int a_rows;                // rows of the A operand kept in shared memory (a multiple of 32, > the last used row)
+  int num_bi;
+  int x_lo, x_cols;          // gathered window of the x row (floats): TMA column coordinate and box width
+  int ne;                    // chunk columns
+  int cta_first, cta_count;  // CTAs [cta_first, cta_first + cta_count) run this part
+  int q_count[4];
+  const int32_t* row_wcol;   // [MT*128] weight column of every A row (-1: zero row)
+  const int32_t* bi_hdr;     // [num_bi][8] {bundle id, mode, nch, mask, quarter, slot0, slot1, slot2}
+  const int32_t* bi_lane;    // [num_bi][32][4] per lane {x offset in the window, out offset of path 0 / 1 / 2 (-1: none)}
+  const int32_t* q_list;     // [4][kTcMaxBI] bundle instances per quarter (heavy first)
+};
 
 struct ConvTcParams {
-  int x_dim, y_dim, out_dim;
-  int num_tiles;             // MT
-  int num_sub;               // sub-items
-  const int32_t* row_wcol;   // [MT*128] weight column of every A row (-1: zero row)
-  const int32_t* sub_hdr;    // [num_sub][8] {type, cpw, lane0 (first TMEM lane within the quarter), tile, quarter, D3,0,0}
-  const int32_t* sub_slot;   // [num_sub][32][4] per lane {xoff, yoff, ooff, valid}
-  const int32_t* q_list;     // [4][kTcMaxSub] sub-item ids per quarter (heavy first)
-  int q_count[4];
+  int x_dim, y_dim, y_lmax, out_dim;
   int nl;
   int sizes[MT_MAX_MLP_LAYERS + 1];
   int act;
   float act_cst;
   const float* w[MT_MAX_MLP_LAYERS];
-  const float* x;
   const float* sh;
   const float* emb;
   const int32_t* rowptr;
@@ -88,10 +88,13 @@ struct ConvTcParams {
   const float* num_neigh;
   float* out;
   int64_t N, E;
-  int y_pad;                   // y_dim rounded up to a multiple of 4 floats
-  __nv_bfloat16* hplanes;      // workspace [3][4][E][8] bf16: plane, k-group, edge, k%8
-  float* ysorted;              // workspace [E][y_pad]
-  long long* dbg;              // optional clock64 stamps of CTA 0 (MT_CONV_TC_DEBUG), else nullptr
+  int num_parts;
+  TcPartParams part[kTcMaxParts];
+  long long* dbg;  // optional phase-timing buffer (mt_conv_set_debug_buffer): [warp][8] clock64 sums of CTA 0
+};
+
+struct alignas(64) TcMaps {
+  CUtensorMap m[kTcMaxParts];  // x as a 2D tensor [N][x_dim], box {x_cols, 1}: one per part (its column window)
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -107,7 +110,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug (or a faulted bulk copy) must end in a trap with a message, never in a hang.
+// Bounded wait: a protocol bug (or a faulted copy) must end in a trap with a message, never in a hang.
 __device__ __noinline__ void mbar_timeout(int id, uint32_t parity) {
   printf("[matten_b200] mbarrier wait timed out: barrier %d parity %u block %d warp %d\n", id, parity, (int)blockIdx.x,
          (int)(threadIdx.x >> 5));
@@ -122,16 +125,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int id
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(2000u)  // suspend-time hint (ns): the warp sleeps in hardware instead of polling
         : "memory");
-    if (!done && (++spins & 63u) == 0) {  // ~2 s at 2 GHz: far beyond any legitimate wait in this kernel
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) mbar_timeout(id, parity);
+    if (!done) {
+      // back off: the issue arbiter favours high warp ids, a waiter that polls at full rate starves the working
+      // warps of its scheduler (measured: 20 cycles per instruction for the producers with polling consumers)
+      __nanosleep(spins < 8 ? 40 : 200);
+      if ((++spins & 1023u) == 0) {  // ~2 s: far beyond any legitimate wait in this kernel
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ll) mbar_timeout(id, parity);
+      }
     }
   } while (!done);
 }
@@ -163,24 +171,38 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// tcgen05.ld is asynchronous: the destination registers are valid only after tcgen05.wait::ld.  The wait takes
-// the registers as read-write operands so the compiler cannot move a use above it.  (Scalars, not arrays:
-// arrays passed through asm operands end up in local memory.)
-#define MT_TMEM_LD_X4(taddr, r0, r1, r2, r3)                                       \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"     \
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)                            \
-               : "r"(taddr)                                                        \
-               : "memory")
-#define MT_TMEM_LD_WAIT(r0, r1, r2, r3) \
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3)::"memory")
+// tcgen05.ld is asynchronous: the destination registers are valid only after tcgen05.wait::ld.  The wait (and the
+// empty "touch" statements for further register groups) take the registers as read-write operands so the compiler
+// cannot move a use above it.  (Scalars, not arrays: arrays passed through asm operands end up in local memory.)
+struct W4 {
+  uint32_t a, b, c, d;
+};
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, W4& r) {  // lane == TMEM lane, 4 consecutive columns
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.a), "=r"(r.b), "=r"(r.c), "=r"(r.d)
+               : "r"(taddr));
+}
+// 16 lanes x 8 columns: thread 4 r + ph gets (lane r: columns 2 ph, 2 ph + 1; lane r + 8: the same columns)
+__device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, W4& r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.a), "=r"(r.b), "=r"(r.c), "=r"(r.d)
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(W4& r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r.a), "+r"(r.b), "+r"(r.c), "+r"(r.d));
+}
+__device__ __forceinline__ void tmem_ld_touch(W4& r) {  // no instruction: orders uses of r after the preceding wait
+  asm volatile("" : "+r"(r.a), "+r"(r.b), "+r"(r.c), "+r"(r.d));
+}
 
-// bulk asynchronous copy global -> shared (the non-tensor TMA path); completes bytes on an mbarrier.
-// size and both addresses are multiples of 16 bytes.
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// TMA tile::gather4: rows r0..r3 of the 2D tensor, columns [col, col + box) -> 4 consecutive rows of shared memory
+__device__ __forceinline__ void tma_gather4(void* dst_smem, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::1 "
+      "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(smem_u32(dst_smem)),
+      "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      : "memory");
 }
 
 // K-major, no-swizzle ("interleave") shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
@@ -207,294 +229,373 @@ __device__ __forceinline__ void split_bf16x3(float v, __nv_bfloat16& hi, __nv_bf
   lo = __float2bfloat16_rn(r2);
 }
 
+// phase timing of CTA 0 (only when a debug buffer is set): TACC(i) adds the cycles since the last stamp to slot i
+#define MT_TC_TIMER() const bool _tm = (p.dbg != nullptr) && blockIdx.x == 0; unsigned _tl = _tm ? (unsigned)clock() : 0u; unsigned _ta[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define MT_TACC(i) do { if (_tm) { const unsigned _n = (unsigned)clock(); _ta[i] += (_n - _tl) >> 4; _tl = _n; } } while (0)
+#define MT_TC_TIMER_FLUSH() do { if (_tm && lane == 0) { for (int _i = 0; _i < 8; ++_i) p.dbg[warp * 8 + _i] = (long long)_ta[_i] << 4; } } while (0)
+
 struct __align__(16) TcMeta {
   int nnodes;  // -1: terminate
   int ncols;   // used (padded) columns; 0: only nodes without edges
-  int pad0, pad1;
+  int continues;  // 1: the first node of the chunk continues a node split over chunks
+  int pad1;
   int node_id[kTcMaxNodes];
-  float den[kTcMaxNodes];            // sqrt(avg_num_neighbors) or sqrt(num_neigh[node])
+  float inv_den[kTcMaxNodes];        // 1 / sqrt(avg_num_neighbors) or 1 / sqrt(num_neigh[node])
   short cb[kTcMaxNodes];             // first column of the node (multiple of 4)
   short ngrp[kTcMaxNodes];           // padded edge count / 4
+  int blk_next;                      // next 8-column block of the chunk nobody has claimed yet (MLP warps)
   unsigned char first[kTcMaxNodes];  // 1: this chunk holds the node's first edges (plain store), 0: accumulate
-  int rlo[kTcMaxNodes];              // first receiver-sorted edge of the node's piece in this chunk
-  int deg[kTcMaxNodes];              // its (unpadded) edge count
 };
 
-// packed per-lane slot of a sub-item (8 bytes)
-struct __align__(8) TcSlot {
-  unsigned short xoff;
-  unsigned char yoff;
-  unsigned char valid;
-  int ooff;
-};
-
-// shared-memory carve-up (bytes)
+// shared-memory carve-up (bytes); every sub-buffer starts at a multiple of 128
 struct TcSmemLayout {
-  size_t a_off, a_plane;  // 3 planes of [MT*128 x 32] bf16
-  size_t b_off, b_plane;  // 3 planes of [64 x 32] bf16
-  size_t x_off, x_buf;    // 2 buffers [64][x_dim] fp32
-  size_t y_off, y_buf;    // 2 buffers [64][y_pad] fp32
-  size_t meta_off;        // 2 TcMeta
-  size_t slot_off;        // [num_sub][32] TcSlot
-  size_t hdr_off;         // [num_sub] packed {type, cpw, lane0, tile, D3}
-  size_t qlist_off;       // [4][kTcMaxSub] uint8
+  size_t a_off, a_plane;  // 3 planes of [a_rows x 32] bf16 (the MMAs of the last tile read past a_rows into the next
+                          // plane / the B planes: rows nobody uses)
+  size_t b_off, b_plane;  // 3 planes of [NE x 32] bf16
+  size_t x_off, x_buf;    // 2 buffers [NE][x_cols] fp32
+  size_t y_off, y_buf;    // 2 buffers [NE/2][2 * y_pad] fp32 (pair-interleaved sh rows)
+  size_t w_off;           // hidden-layer weights, pre-scaled: [w_rows][32] fp32 (layer 0 rows, then layer 1 rows)
+  size_t v_off;           // per MLP warp: [8 columns][33] fp32 layer inputs / outputs (stride 33: conflict-free)
+  size_t meta_off;        // kTcMetaSlots TcMeta
+  size_t cole_off;        // kTcMetaSlots x [3][NE] int per column: receiver-sorted edge (or pad marker), sender row, original edge
+  size_t lane_off;        // [num_bi][32] int4
+  size_t hdr_off;         // [num_bi][8] int
+  size_t qlist_off;       // [4][kTcMaxBI] uint8
   size_t total;
 };
-__host__ __device__ inline size_t tc_align16(size_t v) { return (v + 15) & ~(size_t)15; }
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int MT, int x_dim, int y_pad, int num_sub, int NE) {
+__host__ __device__ inline size_t tc_align(size_t v, size_t a = 128) { return (v + a - 1) & ~(a - 1); }
+__host__ __device__ inline int tc_pad8(int v) { return (v + 7) & ~7; }
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int a_rows, int x_cols, int y_pad, int num_bi, int NE, int w_rows) {
   TcSmemLayout L;
   size_t o = 0;
   L.a_off = o;
-  L.a_plane = (size_t)MT * 128 * kTcK * 2;
+  L.a_plane = (size_t)a_rows * kTcK * 2;
   o += 3 * L.a_plane;
   L.b_off = o;
   L.b_plane = (size_t)NE * kTcK * 2;
-  o += 3 * L.b_plane;
+  o = tc_align(o + 3 * L.b_plane);
   L.x_off = o;
-  L.x_buf = (size_t)NE * x_dim * 4;
+  L.x_buf = tc_align((size_t)NE * x_cols * 4);
   o += 2 * L.x_buf;
   L.y_off = o;
-  L.y_buf = (size_t)NE * y_pad * 4;
+  L.y_buf = tc_align((size_t)(NE / 2) * 2 * y_pad * 4);
   o += 2 * L.y_buf;
+  L.w_off = o;
+  o = tc_align(o + (size_t)w_rows * kTcK * 4);
+  L.v_off = o;
+  o = tc_align(o + (size_t)kTcMlpWarps * 8 * 33 * 4);
   L.meta_off = o;
-  o += 2 * tc_align16(sizeof(TcMeta));
-  L.slot_off = o;
-  o += (size_t)num_sub * 32 * sizeof(TcSlot);
+  o = tc_align(o + kTcMetaSlots * tc_align(sizeof(TcMeta), 16));
+  L.cole_off = o;
+  o = tc_align(o + kTcMetaSlots * 3 * (size_t)NE * 4);
+  L.lane_off = o;
+  o += (size_t)num_bi * 32 * 16;
   L.hdr_off = o;
-  o += tc_align16((size_t)num_sub * 4);
+  o += (size_t)num_bi * 32;
   L.qlist_off = o;
-  o += 4 * kTcMaxSub;
+  o = tc_align(o + 4 * kTcMaxBI);
   L.total = o;
   return L;
 }
 
 // =====================================================================================================
-// (1) per-edge preparation: hidden layers of the radial MLP -> bf16 planes, sh row -> 16-byte padded row
+// consumer units
 // =====================================================================================================
-constexpr int kPrepThreads = 128;
+struct TcUnit {
+  uint32_t tstage;    // TMEM address of the stage: base + b * MT * NE columns (lane field 0)
+  int quarter;        // TMEM lanes 32 * quarter ..
+  int ne;             // chunk columns
+  int slot[3];        // per path: 2 * tile + half
+  unsigned mask;      // active paths
+  int nch;            // mode P: channels per row block (8 / 4 / 2)
+  const float* xs;    // staged x rows of the chunk [NE][xstride]
+  int xstride;
+  const float* ys;    // staged pair-interleaved sh rows [NE/2][ystride]
+  int ystride;        // floats per edge pair
+  int cb, ngrp;       // the node's first column and number of 4-column groups
+  int4 lt;            // lane table entry {x offset, out offsets}
+  float* out;         // the node's output row
+  float inv_den;
+  bool first;
+};
 
-__global__ void __launch_bounds__(kPrepThreads) edge_prepare_kernel(const ConvTcParams p) {
-  // weights of the hidden layers (pre-scaled by 1/sqrt(fan_in)) and one private activation row per thread
-  __shared__ __align__(16) float sW[2][kTcK * kTcK];
-  __shared__ float sH[kPrepThreads][kTcK + 1];
-  const int nh = p.nl - 1;
-  for (int li = 0; li < nh; ++li) {
-    const int fi = p.sizes[li], fo = p.sizes[li + 1];
-    const float s = rsqrtf((float)fi);
-    for (int t = threadIdx.x; t < kTcK * kTcK; t += kPrepThreads) {
-      const int k = t >> 5, j = t & 31;
-      sW[li][t] = (k < fi && j < fo) ? p.w[li][(size_t)k * fo + j] * s : 0.f;
-    }
-  }
-  __syncthreads();
-  const int in0 = p.sizes[0];
-  float* hrow = sH[threadIdx.x];
-  for (int64_t e = blockIdx.x * (int64_t)kPrepThreads + threadIdx.x; e < p.E; e += (int64_t)gridDim.x * kPrepThreads) {
-    const int64_t orig = p.perm[e];
-    // sh row, padded
-    {
-      // loads first, stores after: a store waiting for its load would block the next load behind it (in-order issue)
-      const float* __restrict__ yr = p.sh + orig * p.y_dim;
-      float* __restrict__ yo = p.ysorted + e * p.y_pad;
-      for (int j0 = 0; j0 < p.y_pad; j0 += 12) {
-        float yv[12];
+// (TcUnit travels BY VALUE through force-inlined functions: a unit kept in local memory costs an L2 round trip per
+//  field access, the 227 KB shared-memory carve-out leaves almost no L1)
+template <class B>
+__device__ __forceinline__ void tc_store(const f2* __restrict__ acc, const TcUnit u, unsigned mask) {
+  const int oo[3] = {u.lt.y, u.lt.z, u.lt.w};
 #pragma unroll
-        for (int j = 0; j < 12; ++j) yv[j] = (j0 + j < p.y_dim) ? yr[j0 + j] : 0.f;
+  for (int p = 0; p < B::NP; ++p) {
+    if (!((mask >> p) & 1u) || oo[p] < 0) continue;
+    float* o = u.out + oo[p];
 #pragma unroll
-        for (int j = 0; j < 12; j += 4)
-          if (j0 + j < p.y_pad) *reinterpret_cast<float4*>(yo + j0 + j) = make_float4(yv[j], yv[j + 1], yv[j + 2], yv[j + 3]);
-      }
-    }
-    float h[kTcK];
-#pragma unroll
-    for (int j = 0; j < kTcK; ++j) h[j] = 0.f;
-    {
-      const float* er = p.emb + orig * in0;
-#pragma unroll
-      for (int j = 0; j < kTcK; ++j)
-        if (j < in0) h[j] = er[j];
-    }
-    for (int li = 0; li < nh; ++li) {
-      const int fi = p.sizes[li], fo = p.sizes[li + 1];
-#pragma unroll
-      for (int j = 0; j < kTcK; ++j) hrow[j] = h[j];
-      float2 a[kTcK / 2];  // output pairs: one FFMA2 (broadcast h[k]) per pair
-#pragma unroll
-      for (int j = 0; j < kTcK / 2; ++j) a[j] = make_float2(0.f, 0.f);
-      const float* W = sW[li];
-#pragma unroll 4
-      for (int k = 0; k < fi; ++k) {
-        const float hk = hrow[k];
-        const float4* wr = reinterpret_cast<const float4*>(W + k * kTcK);
-#pragma unroll
-        for (int j4 = 0; j4 < kTcK / 4; ++j4) {
-          const float4 w4 = wr[j4];
-          fma_pair(hk, w4.x, w4.y, a[2 * j4]);
-          fma_pair(hk, w4.z, w4.w, a[2 * j4 + 1]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kTcK; ++j) {
-        const float aj = (j & 1) ? a[j >> 1].y : a[j >> 1].x;
-        h[j] = (j < fo) ? apply_act<float>(p.act, aj) * p.act_cst : 0.f;
-      }
-    }
-    // planes [3][4][E][8]
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      __align__(16) __nv_bfloat16 hi[8], mi[8], lo[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) split_bf16x3(h[g * 8 + i], hi[i], mi[i], lo[i]);
-      uint4* base = reinterpret_cast<uint4*>(p.hplanes);
-      base[(size_t)(0 * 4 + g) * p.E + e] = *reinterpret_cast<const uint4*>(hi);
-      base[(size_t)(1 * 4 + g) * p.E + e] = *reinterpret_cast<const uint4*>(mi);
-      base[(size_t)(2 * 4 + g) * p.E + e] = *reinterpret_cast<const uint4*>(lo);
+    for (int m = 0; m < B::path_d3(p); ++m) {
+      const int i = B::path_acc(p) + m;
+      const float v = (acc[i].v.x + acc[i].v.y) * (B::scale(i) * u.inv_den);
+      const float prev = u.first ? 0.f : o[m];  // `first` is warp-uniform; one store either way (compact code)
+      o[m] = prev + v;
     }
   }
 }
 
-// =====================================================================================================
-// (2) fused kernel
-// =====================================================================================================
+template <class B>
+__device__ __forceinline__ void tc_load_xy(const TcUnit u, int col, f2* __restrict__ x2, f2* __restrict__ y2) {
+  const float* xr = u.xs + (size_t)col * u.xstride + u.lt.x;
+#pragma unroll
+  for (int m = 0; m < B::D1; ++m) x2[m] = f2(xr[m], xr[u.xstride + m]);
+  const float4* yr = reinterpret_cast<const float4*>(u.ys + (size_t)(col >> 1) * u.ystride + 2 * B::Y_LO);
+#pragma unroll
+  for (int i = 0; i < B::Y_CNT / 2; ++i) {
+    const float4 v = yr[i];
+    y2[2 * i] = f2(v.x, v.y);
+    y2[2 * i + 1] = f2(v.z, v.w);
+  }
+}
 
-// One (sub-item, node) unit for one (l1,l2,l3) type: ngrp groups of 4 columns starting at column cb.
-// Compact on purpose (2 inlined contractions for lane==row items, 1 for packed items): the hot code of 28 warps
-// on different types has to stay in the instruction cache (fully unrolled per-type loops measured a 74 % I-cache
-// hit rate with the GPC instruction cache at 86 % of its request peak).
-template <int L1, int L2, int L3>
-__device__ __forceinline__ void tc_unit(uint32_t taddr, const float* __restrict__ xp, int xstride,
-                                        const float* __restrict__ yp, int ystride, int ngrp, int cpw, int lane,
-                                        int src_lane, float* __restrict__ acc) {
-  constexpr int D1 = 2 * L1 + 1, D2 = 2 * L2 + 1;
-  uint32_t c0, c1, c2, c3, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-  MT_TMEM_LD_X4(taddr, c0, c1, c2, c3);
-  MT_TMEM_LD_WAIT(c0, c1, c2, c3);
-  if (cpw == 32) {
-    // lane == TMEM row: every lane walks all columns, two edges per iteration packed into FFMA2 / FMUL2 (edge a in
-    // the low half, edge b in the high half of every register pair); the two partial sums are added at the end
-    constexpr int D3 = 2 * L3 + 1;
-    f2 acc2[D3];
+// Both unit loops are kept SMALL on purpose (one edge pair per iteration, no per-path branches when every path of the
+// bundle exists): five warps per scheduler run five different instruction streams, and a loop body that does not stay
+// in the instruction cache stalls on every 128-byte line (ncu: `no_instruction` was the top stall of the unrolled form).
+struct W2 {
+  uint32_t a, b;
+};
+__device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, W2& r) {  // lane == TMEM lane, 2 consecutive columns
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r.a), "=r"(r.b) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait2(W2& r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r.a), "+r"(r.b));
+}
+__device__ __forceinline__ void tmem_ld_touch2(W2& r) { asm volatile("" : "+r"(r.a), "+r"(r.b)); }
+
+// mode L: lane == channel; every lane walks all edge pairs of the node, two edges per FFMA2
+template <class B, bool FULL>
+__device__ __forceinline__ void tc_unit_L(const TcUnit u) {
+  constexpr unsigned kAll = (1u << B::NP) - 1u;
+  const unsigned mask = FULL ? kAll : u.mask;
+  f2 acc[B::NACC];
 #pragma unroll
-    for (int m = 0; m < D3; ++m) acc2[m] = f2(0.f, 0.f);
-    auto two_edges = [&](const f2 w2) {
-      f2 x2[D1], y2[D2];
+  for (int i = 0; i < B::NACC; ++i) acc[i] = f2(0.f, 0.f);
+  const uint32_t tq = u.tstage + ((uint32_t)(32 * u.quarter) << 16) + (uint32_t)u.cb;
+  uint32_t ta[B::NP];
 #pragma unroll
-      for (int m = 0; m < D1; ++m) x2[m] = f2(xp[m], xp[xstride + m]);
+  for (int p = 0; p < B::NP; ++p) ta[p] = tq + (uint32_t)((u.slot[p] >> 1) * u.ne);
+  W2 wc[B::NP], wn[B::NP];
 #pragma unroll
-      for (int m = 0; m < D2; ++m) y2[m] = f2(yp[m], yp[ystride + m]);
-      CG<L1, L2, L3>::template fwd<f2>(x2, y2, w2, acc2);
-      xp += 2 * xstride;
-      yp += 2 * ystride;
-    };
+  for (int p = 0; p < B::NP; ++p) {
+    wc[p].a = wc[p].b = 0u;
+    wn[p] = wc[p];
+  }
+  const int npairs = 2 * u.ngrp;
+  if (npairs > 0) {
+#pragma unroll
+    for (int p = 0; p < B::NP; ++p)
+      if ((mask >> p) & 1u) tmem_ld_x2(ta[p], wc[p]);
+    tmem_ld_wait2(wc[0]);
+#pragma unroll
+    for (int p = 1; p < B::NP; ++p) tmem_ld_touch2(wc[p]);
+  }
 #pragma unroll 1
-    for (int g = 0; g < ngrp; ++g) {
-      const bool more = g + 1 < ngrp;
-      if (more) MT_TMEM_LD_X4(taddr + (uint32_t)(4 * g + 4), n0, n1, n2, n3);  // prefetch the next 4 columns
-      // (rolled on purpose: straight-line code for the 4 columns of a group measured 4 % slower -- instruction fetch)
+  for (int g = 0; g < npairs; ++g) {
+    const bool more = g + 1 < npairs;
+    if (more) {
+#pragma unroll
+      for (int p = 0; p < B::NP; ++p)
+        if ((mask >> p) & 1u) tmem_ld_x2(ta[p] + (uint32_t)(2 * g + 2), wn[p]);  // prefetch the next pair's weights
+    }
+    f2 x2[B::D1], y2[B::Y_CNT], w2[B::NP];
+    tc_load_xy<B>(u, u.cb + 2 * g, x2, y2);
+#pragma unroll
+    for (int p = 0; p < B::NP; ++p) w2[p] = f2(__uint_as_float(wc[p].a), __uint_as_float(wc[p].b));
+    B::template edge<f2>(x2, y2, w2, acc, mask);
+    if (more) {
+      tmem_ld_wait2(wn[0]);
+#pragma unroll
+      for (int p = 1; p < B::NP; ++p) tmem_ld_touch2(wn[p]);
+#pragma unroll
+      for (int p = 0; p < B::NP; ++p) wc[p] = wn[p];
+    }
+  }
+  tc_store<B>(acc, u, mask);
+}
+
+// mode P: thread 4 r + ph: channel r % nch, edge pairs ph + 4 (r / nch) of every block of 32 / nch pairs
+template <class B, bool FULL>
+__device__ __forceinline__ void tc_unit_P(const TcUnit u, int lane) {
+  constexpr int NPAIR = (B::NP + 1) / 2;
+  constexpr unsigned kAll = (1u << B::NP) - 1u;
+  const unsigned mask = FULL ? kAll : u.mask;
+  f2 acc[B::NACC];
+#pragma unroll
+  for (int i = 0; i < B::NACC; ++i) acc[i] = f2(0.f, 0.f);
+  const int r8 = lane >> 2, ph = lane & 3;
+  const int lg = (u.nch == 8) ? 3 : (u.nch == 4 ? 2 : 1);
+  const int sub = r8 >> lg, dup = 8 >> lg;
+  const int block = 8 * dup, ncols = 4 * u.ngrp;
+  uint32_t ta[NPAIR];
+#pragma unroll
+  for (int j = 0; j < NPAIR; ++j) {
+    const int s = u.slot[2 * j];  // both paths of a pair share the half slot
+    ta[j] = u.tstage + ((uint32_t)(32 * u.quarter + 16 * (s & 1)) << 16) + (uint32_t)((s >> 1) * u.ne);
+  }
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) two_edges(f2(__uint_as_float(h ? c2 : c0), __uint_as_float(h ? c3 : c1)));
-      if (more) {
-        MT_TMEM_LD_WAIT(n0, n1, n2, n3);
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+  for (int start = u.cb; start < u.cb + ncols; start += block) {
+    const int cstart = min(start, u.ne - block);  // keep the TMEM read inside the stage
+    W4 wsel[NPAIR];
+#pragma unroll
+    for (int j = 0; j < NPAIR; ++j) {
+      wsel[j].a = wsel[j].b = wsel[j].c = wsel[j].d = 0u;
+      if (!((mask >> (2 * j)) & 3u)) continue;  // neither path of the pair exists (warp uniform)
+#pragma unroll 1
+      for (int d = 0; d < dup; ++d) {
+        W4 t;
+        tmem_ld_16x256b(ta[j] + (uint32_t)(cstart + 8 * d), t);
+        tmem_ld_wait(t);
+        if (d == sub) wsel[j] = t;
       }
     }
+    const int mycol = cstart + 8 * sub + 2 * ph;
+    const bool active = mycol >= start && mycol < u.cb + ncols;
+    f2 x2[B::D1], y2[B::Y_CNT], w2[B::NP];
+    tc_load_xy<B>(u, active ? mycol : u.cb, x2, y2);
 #pragma unroll
-    for (int m = 0; m < D3; ++m) acc[m] += acc2[m].v.x + acc2[m].v.y;
+    for (int p = 0; p < B::NP; ++p) {
+      const W4& t = wsel[p >> 1];
+      const float w0 = __uint_as_float((p & 1) ? t.c : t.a), w1 = __uint_as_float((p & 1) ? t.d : t.b);
+      w2[p] = active ? f2(w0, w1) : f2(0.f, 0.f);
+    }
+    B::template edge<f2>(x2, y2, w2, acc, mask);
+    __syncwarp();
+  }
+  // fixed-order butterfly over the edge phases (lane bits 0-1) and the duplicate row blocks (lane bits 2+lg ..)
+#pragma unroll
+  for (int i = 0; i < B::NACC; ++i) {
+    float s = acc[i].v.x + acc[i].v.y;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    for (int o = 4 << lg; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    acc[i] = f2(s, 0.f);
+  }
+  tc_store<B>(acc, u, mask);
+}
+
+template <int ID>
+__device__ __forceinline__ void tc_unit_dispatch(const TcUnit u, int mode, int lane) {
+  using B = Bundle<ID>;
+  const bool full = u.mask == (1u << B::NP) - 1u;
+  if (mode == 0) {
+    if (full) tc_unit_L<B, true>(u);
+    else tc_unit_L<B, false>(u);
   } else {
-    // packed small types: lane = (column j, phase ph); phase ph takes the columns == ph (mod nphase) of every
-    // group and fetches its weight from the lane that owns the column's TMEM row
-    const int nphase = 32 / cpw, phase = lane / cpw;
-    xp += phase * xstride;
-    yp += phase * ystride;
-#pragma unroll 1
-    for (int g = 0; g < ngrp; ++g) {
-      const bool more = g + 1 < ngrp;
-      if (more) MT_TMEM_LD_X4(taddr + (uint32_t)(4 * g + 4), n0, n1, n2, n3);
-      const float t0 = __shfl_sync(0xffffffffu, __uint_as_float(c0), src_lane);
-      const float t1 = __shfl_sync(0xffffffffu, __uint_as_float(c1), src_lane);
-      const float t2 = __shfl_sync(0xffffffffu, __uint_as_float(c2), src_lane);
-      const float t3 = __shfl_sync(0xffffffffu, __uint_as_float(c3), src_lane);
-      // warp-uniform trip count (r), lane-dependent column j = r + phase selected without branches: the warp
-      // must be converged when it reaches the next .sync.aligned TMEM instruction
-#pragma unroll 1
-      for (int r = 0; r < 4; r += nphase) {
-        const int j = r + phase;
-        const float w = (j == 0) ? t0 : (j == 1) ? t1 : (j == 2) ? t2 : t3;
-        const float* xr = xp + r * xstride;
-        const float* yr = yp + r * ystride;
-        float xa[D1], ya[D2];
-#pragma unroll
-        for (int m = 0; m < D1; ++m) xa[m] = xr[m];
-#pragma unroll
-        for (int m = 0; m < D2; ++m) ya[m] = yr[m];
-        CG<L1, L2, L3>::template fwd<float>(xa, ya, w, acc);
-      }
-      xp += 4 * xstride;
-      yp += 4 * ystride;
-      __syncwarp();
-      if (more) {
-        MT_TMEM_LD_WAIT(n0, n1, n2, n3);
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-      }
-    }
+    if (full) tc_unit_P<B, true>(u, lane);
+    else tc_unit_P<B, false>(u, lane);
   }
 }
 
-template <int NE>
-__global__ void __launch_bounds__(tc_threads(NE), 1) conv_fwd_tc_kernel(const ConvTcParams p) {
-  constexpr int kTcConsumerWarps = tc_consumer_warps(NE), kTcThreads = tc_threads(NE);
-  extern __shared__ __align__(128) unsigned char smem[];  // no swizzle: descriptors need 16 B alignment
-  __shared__ uint64_t bar_full[2], bar_empty[2], bar_go[2], bar_bready, bar_bfree;
+// =====================================================================================================
+// radial MLP pieces (producer warps)
+// =====================================================================================================
+// sigmoid through the special-function unit: ex2.approx (2 ulp) and rcp.approx (1 ulp); relative error ~3e-7
+__device__ __forceinline__ float tc_fast_sigmoid(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * v));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+// hi / mid / lo bf16 planes of 8 floats (v = hi + mid + lo to ~2^-24), packed conversions (two values per F2FP)
+__device__ __forceinline__ void tc_split8(const float (&v)[8], uint4& hi, uint4& mi, uint4& lo) {
+  uint32_t H[4], M[4], Lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = v[2 * i], b = v[2 * i + 1];
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+    const float ra = a - __uint_as_float(hb << 16), rb = b - __uint_as_float(hb & 0xffff0000u);
+    const __nv_bfloat162 m2 = __floats2bfloat162_rn(ra, rb);
+    const uint32_t mb = *reinterpret_cast<const uint32_t*>(&m2);
+    const float sa = ra - __uint_as_float(mb << 16), sb = rb - __uint_as_float(mb & 0xffff0000u);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(sa, sb);
+    H[i] = hb;
+    M[i] = mb;
+    Lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  hi = make_uint4(H[0], H[1], H[2], H[3]);
+  mi = make_uint4(M[0], M[1], M[2], M[3]);
+  lo = make_uint4(Lo[0], Lo[1], Lo[2], Lo[3]);
+}
+__device__ __forceinline__ float tc_act(int act, float v) {
+  if (act == MT_ACT_SILU) return v * tc_fast_sigmoid(v);
+  if (act == MT_ACT_SIGMOID) return tc_fast_sigmoid(v);
+  return apply_act<float>(act, v);
+}
+
+// =====================================================================================================
+// the kernel.  LMAXK: largest degree of the bundles compiled in (2: l <= 2 layers, 4: everything)
+// =====================================================================================================
+template <int LMAXK>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid_constant__ ConvTcParams p,
+                                                                   const __grid_constant__ TcMaps maps) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar_full[2], bar_empty[2], bar_bready[2], bar_go[kTcMetaSlots], bar_mfree[kTcMetaSlots], bar_bfree;
   __shared__ uint32_t s_tmem_base;
   __shared__ int s_cnt[2][4];
-  __shared__ int s_mma_b;  // buffer of the chunk handed to the MMA warp (-1: terminate)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int MT = p.num_tiles;
-  const TcSmemLayout L = tc_smem_layout(MT, p.x_dim, p.y_pad, p.num_sub, NE);
+  // which part does this CTA run, and which share of the node range
+  int part_id = 0;
+#pragma unroll
+  for (int i = 1; i < kTcMaxParts; ++i)
+    if (i < p.num_parts && (int)blockIdx.x >= p.part[i].cta_first) part_id = i;
+  const TcPartParams& P = p.part[part_id];
+  const int MT = P.num_tiles, NE = P.ne, a_rows = P.a_rows;
+  const int y_pad = sh_pad_len(p.y_lmax);
+  const int ystride = 2 * y_pad;
+  const int nh = p.nl - 1;  // hidden layers (0 .. 2)
+  const int wrow1 = nh > 0 ? tc_pad8(p.sizes[0]) : 0;  // rows of layer 0 in sW; layer 1 follows
+  const int w_rows = wrow1 + (nh > 1 ? tc_pad8(p.sizes[1]) : 0);
+  const TcSmemLayout L = tc_smem_layout(a_rows, P.x_cols, y_pad, P.num_bi, NE, w_rows);
   unsigned char* sA = smem + L.a_off;
   unsigned char* sB = smem + L.b_off;
-  TcMeta* meta0 = reinterpret_cast<TcMeta*>(smem + L.meta_off);
-  TcMeta* meta1 = reinterpret_cast<TcMeta*>(smem + L.meta_off + tc_align16(sizeof(TcMeta)));
-  TcSlot* sSlot = reinterpret_cast<TcSlot*>(smem + L.slot_off);
-  uint32_t* sHdr = reinterpret_cast<uint32_t*>(smem + L.hdr_off);
+  float* sW = reinterpret_cast<float*>(smem + L.w_off);
+  unsigned char* sMeta = smem + L.meta_off;
+  constexpr size_t kMetaBytes = (sizeof(TcMeta) + 15) & ~(size_t)15;
+  int* sColE = reinterpret_cast<int*>(smem + L.cole_off);
+  int4* sLane = reinterpret_cast<int4*>(smem + L.lane_off);
+  int* sHdr = reinterpret_cast<int*>(smem + L.hdr_off);
   unsigned char* sQ = smem + L.qlist_off;
-  const uint32_t tmem_cols = (2 * MT * NE <= 32) ? 32 : (2 * MT * NE <= 64) ? 64 : (2 * MT * NE <= 128) ? 128
-                             : (2 * MT * NE <= 256) ? 256 : 512;
 
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
-    mbar_init(&bar_full[0], 2);
-    mbar_init(&bar_full[1], 2);
+    mbar_init(&bar_full[0], kTcMlpWarps + 1);  // MLP warps (sh rows written, gather bytes) + the MMA commit
+    mbar_init(&bar_full[1], kTcMlpWarps + 1);
     mbar_init(&bar_empty[0], kTcConsumerWarps);
     mbar_init(&bar_empty[1], kTcConsumerWarps);
-    mbar_init(&bar_go[0], 1);
-    mbar_init(&bar_go[1], 1);
-    mbar_init(&bar_bready, 1);
+    mbar_init(&bar_bready[0], kTcMlpWarps);
+    mbar_init(&bar_bready[1], kTcMlpWarps);
+    for (int i = 0; i < kTcMetaSlots; ++i) {
+      mbar_init(&bar_go[i], 1);
+      mbar_init(&bar_mfree[i], kTcConsumerWarps);
+    }
     mbar_init(&bar_bfree, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&s_tmem_base, tmem_cols);
+  if (warp == 0) tmem_alloc(&s_tmem_base, 512);
   // plan tables -> shared memory (with a ~225 KB carve-out the L1 is a few KB: every global load is an L2 trip)
-  for (int t = tid; t < p.num_sub * 32; t += kTcThreads) {
-    const int4 v = reinterpret_cast<const int4*>(p.sub_slot)[t];
-    TcSlot sl;
-    sl.xoff = (unsigned short)v.x;
-    sl.yoff = (unsigned char)v.y;
-    sl.valid = (unsigned char)v.w;
-    sl.ooff = v.z;
-    sSlot[t] = sl;
+  for (int t = tid; t < P.num_bi * 32; t += kTcThreads) sLane[t] = reinterpret_cast<const int4*>(P.bi_lane)[t];
+  for (int t = tid; t < P.num_bi * 8; t += kTcThreads) sHdr[t] = P.bi_hdr[t];
+  for (int t = tid; t < 4 * kTcMaxBI; t += kTcThreads) sQ[t] = (unsigned char)P.q_list[t];
+  // hidden-layer weights, pre-scaled by 1/sqrt(fan_in), rows padded to a multiple of 8, 32 (zero padded) columns
+  for (int li = 0; li < nh; ++li) {
+    const int fi = p.sizes[li], fo = p.sizes[li + 1];
+    const float s = rsqrtf((float)fi);
+    float* W = sW + (li ? wrow1 : 0) * kTcK;
+    for (int t = tid; t < tc_pad8(fi) * kTcK; t += kTcThreads) {
+      const int k = t >> 5, j = t & 31;
+      W[t] = (k < fi && j < fo) ? p.w[li][(size_t)k * fo + j] * s : 0.f;
+    }
   }
-  for (int t = tid; t < p.num_sub; t += kTcThreads) {
-    const int* h = p.sub_hdr + t * 8;
-    sHdr[t] = (uint32_t)h[0] | ((uint32_t)h[1] << 8) | ((uint32_t)h[2] << 16) | ((uint32_t)(h[3] & 15) << 24) |
-              ((uint32_t)(h[5] & 15) << 28);  // type | cpw | lane0 | tile | D3
-  }
-  for (int t = tid; t < 4 * kTcMaxSub; t += kTcThreads) sQ[t] = (unsigned char)p.q_list[t];
-  // staging buffers start zeroed: pad columns are read (with zero weights) and must hold finite values
+  // staging buffers start zeroed: pad columns / never-written pad positions are read and must hold finite values
   {
     uint4* z = reinterpret_cast<uint4*>(smem + L.b_off);
-    const int n16 = (int)((L.meta_off - L.b_off) >> 4);
+    const int n16 = (int)((L.w_off - L.b_off) >> 4);  // B planes, x and Y buffers
     for (int t = tid; t < n16; t += kTcThreads) z[t] = make_uint4(0u, 0u, 0u, 0u);
   }
   // A planes: rows of W_last^T (pre-scaled by 1/sqrt(H)) split into bf16 hi/mid/lo, canonical K-major layout
@@ -502,10 +603,9 @@ __global__ void __launch_bounds__(tc_threads(NE), 1) conv_fwd_tc_kernel(const Co
     const int H = p.sizes[p.nl - 1], Wn = p.sizes[p.nl];
     const float* __restrict__ Wl = p.w[p.nl - 1];
     const float s = rsqrtf((float)H);
-    const int rows = MT * 128;
-    for (int t = tid; t < rows * 4; t += kTcThreads) {
+    for (int t = tid; t < a_rows * 4; t += kTcThreads) {
       const int R = t >> 2, g = t & 3;
-      const int wc = p.row_wcol[R];
+      const int wc = P.row_wcol[R];
       __align__(16) __nv_bfloat16 hi[8], mi[8], lo[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -513,7 +613,7 @@ __global__ void __launch_bounds__(tc_threads(NE), 1) conv_fwd_tc_kernel(const Co
         const float v = (wc >= 0 && k < H) ? Wl[(size_t)k * Wn + wc] * s : 0.f;
         split_bf16x3(v, hi[i], mi[i], lo[i]);
       }
-      const size_t off = (size_t)g * rows * 16 + (size_t)R * 16;
+      const size_t off = (size_t)g * a_rows * 16 + (size_t)R * 16;
       *reinterpret_cast<uint4*>(sA + off) = *reinterpret_cast<const uint4*>(hi);
       *reinterpret_cast<uint4*>(sA + L.a_plane + off) = *reinterpret_cast<const uint4*>(mi);
       *reinterpret_cast<uint4*>(sA + 2 * L.a_plane + off) = *reinterpret_cast<const uint4*>(lo);
@@ -525,15 +625,16 @@ __global__ void __launch_bounds__(tc_threads(NE), 1) conv_fwd_tc_kernel(const Co
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
-  if (warp == 0) {
-    // ================================================================ chunk builder + bulk copies
-    // node range of this CTA: boundaries at equal shares of the edge list
-    int64_t n_cur, n_end;
+  if (warp == kTcControlWarp) {
+    // ================================================================ control: scheduler + TMA gathers + MMA issue
+    int64_t n_cur = 0, n_end = 0;
+    int e_carry = -1;  // >= 0: the next chunk continues node n_cur at this receiver-sorted edge
     {
-      auto bound = [&](int64_t i) -> int64_t {  // first node whose rowptr >= i*E/grid
+      const int64_t rank = (int64_t)blockIdx.x - P.cta_first, cnt = P.cta_count;
+      auto bound = [&](int64_t i) -> int64_t {  // first node whose rowptr >= i*E/cnt
         if (i <= 0) return 0;
-        if (i >= (int64_t)gridDim.x) return p.N;
-        const int64_t target = (p.E * i) / gridDim.x;
+        if (i >= cnt) return p.N;
+        const int64_t target = (p.E * i) / cnt;
         int64_t lo = 0, hi = p.N;
         while (lo < hi) {
           const int64_t mid = (lo + hi) >> 1;
@@ -542,348 +643,430 @@ __global__ void __launch_bounds__(tc_threads(NE), 1) conv_fwd_tc_kernel(const Co
         return lo;
       };
       if (p.E == 0) {
-        n_cur = (p.N * blockIdx.x) / gridDim.x;
-        n_end = (p.N * (blockIdx.x + 1)) / gridDim.x;
+        n_cur = (p.N * rank) / cnt;
+        n_end = (p.N * (rank + 1)) / cnt;
       } else {
-        n_cur = bound(blockIdx.x);
-        n_end = bound(blockIdx.x + 1);
+        n_cur = bound(rank);
+        n_end = bound(rank + 1);
       }
     }
-    int e_carry = -1;  // >= 0: the next chunk continues node n_cur at this global edge
-    int b_uses = 0;    // chunks that loaded the h planes so far
-    MT_TIMING_ONLY(long long _tl = clock64(), t_we = 0, t_meta = 0, t_wb = 0, t_pad = 0, t_issue = 0;)
-    long long n_chunks = 0;
-    const uint32_t xrow_bytes = (uint32_t)p.x_dim * 4, yrow_bytes = (uint32_t)p.y_pad * 4;
-    for (int k = 0;; ++k) {
-      const int b = k & 1;
-      TcMeta& M = b ? *meta1 : *meta0;
-      MT_DBG(1000 + k * 10 + 0);
+    bool sched_done = false;
+    int k_sched = 0;  // chunks published so far
+    // window of 32 consecutive row pointers (lane l: rowptr[w_base + l]) = 31 nodes: reloaded every ~16 nodes, so most
+    // chunks are scheduled without a global-memory round trip
+    int64_t w_base = n_cur;
+    int w_ptr = (w_base + lane <= p.N) ? p.rowptr[w_base + lane] : 0;
+    // publishes the metadata of chunk k_sched (slot k_sched % kTcMetaSlots; see the calls for why the slot is free)
+    auto schedule = [&]() {
+      const int ms = k_sched % kTcMetaSlots;
+      TcMeta& M = *reinterpret_cast<TcMeta*>(sMeta + ms * kMetaBytes);
+      int* cole = sColE + ms * 3 * NE;
       if (n_cur >= n_end) {
-        if (lane == 0) mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);  // consumers released buffer b
-        __syncwarp();
         if (lane == 0) {
           M.nnodes = -1;
           M.ncols = 0;
-          mbar_arrive(&bar_go[b]);  // the x-row warps see the terminator
-          if (b_uses > 0) mbar_wait(&bar_bfree, (b_uses - 1) & 1, 20);  // the MMA warp is done with its last chunk
-          s_mma_b = -1;
-          mbar_arrive(&bar_bready);  // terminator for the MMA warp
+          M.blk_next = 0;
+        }
+        sched_done = true;
+      } else {
+        if (n_cur - w_base > 15) {
+          w_base = n_cur;
+          w_ptr = (w_base + lane <= p.N) ? p.rowptr[w_base + lane] : 0;
+        }
+        const int off = (int)(n_cur - w_base);
+        const int64_t cand = n_cur + lane;  // lane l looks at node n_cur + l
+        const bool in_range = cand < n_end && off + lane < 31;
+        int r_lo = __shfl_sync(0xffffffffu, w_ptr, (off + lane) & 31);
+        const int r_hi = __shfl_sync(0xffffffffu, w_ptr, (off + lane + 1) & 31);
+        if (lane == 0 && e_carry >= 0) r_lo = e_carry;
+        int deg = in_range ? r_hi - r_lo : 0;
+        bool split = false;
+        if (lane == 0 && deg > NE) {  // node larger than a chunk: take NE edges now, the rest next time
+          deg = NE;
+          split = true;
+        }
+        const int degp = (deg + 3) & ~3;
+        int cum = in_range ? degp : 0x10000;  // inclusive prefix of padded degrees
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, cum, o);
+          if (lane >= o) cum += t;
+        }
+        const unsigned fm = __ballot_sync(0xffffffffu, in_range && cum <= NE);
+        int m = (fm == 0xffffffffu) ? 32 : (__ffs(~fm) - 1);  // leading run of nodes that fit
+        const bool split0 = __shfl_sync(0xffffffffu, (int)split, 0) != 0;
+        if (split0) m = 1;
+        const bool mine = lane < m;
+        const int cb = cum - degp;
+        const int ncols = __shfl_sync(0xffffffffu, cum, m - 1);
+        if (mine) {
+          M.node_id[lane] = (int)cand;
+          M.cb[lane] = (short)cb;
+          M.ngrp[lane] = (short)(degp >> 2);
+          M.first[lane] = (lane == 0 && e_carry >= 0) ? 0 : 1;
+          M.inv_den[lane] = p.num_neigh ? rsqrtf(p.num_neigh[cand]) : rsqrtf(p.avg);
+        }
+        if (lane == 0) {
+          M.nnodes = m;
+          M.ncols = ncols;
+          M.continues = (e_carry >= 0) ? 1 : 0;
+          M.blk_next = 0;
+        }
+        // per column: receiver-sorted edge (e >= 0 real edge, -2 - e: pad column = zero weights, operands of edge e),
+        // and -- resolved here, chunks ahead of their use -- the sender row and the original edge id
+        for (int j = 0; j < m; ++j) {
+          const int dj = __shfl_sync(0xffffffffu, deg, j), cj = __shfl_sync(0xffffffffu, cb, j);
+          const int rj = __shfl_sync(0xffffffffu, r_lo, j);
+          const int dpj = (dj + 3) & ~3;
+          for (int t = lane; t < dpj; t += 32) cole[cj + t] = (t < dj) ? (rj + t) : (-2 - (rj + dj - 1));
+        }
+        __syncwarp();
+        for (int c0 = 0; c0 < ncols; c0 += 64) {  // all global loads of (up to) 64 columns in flight together
+          const int c1 = c0 + lane, c2 = c0 + 32 + lane;
+          int e1 = c1 < ncols ? cole[c1] : 0, e2 = c2 < ncols ? cole[c2] : 0;
+          e1 = e1 >= 0 ? e1 : (-2 - e1);
+          e2 = e2 >= 0 ? e2 : (-2 - e2);
+          int s1 = 0, o1 = 0, s2 = 0, o2 = 0;
+          if (c1 < ncols) { s1 = p.src[e1]; o1 = p.perm[e1]; }
+          if (c2 < ncols) { s2 = p.src[e2]; o2 = p.perm[e2]; }
+          if (c1 < ncols) { cole[NE + c1] = s1; cole[2 * NE + c1] = o1; }
+          if (c2 < ncols) { cole[NE + c2] = s2; cole[2 * NE + c2] = o2; }
+        }
+        if (split0) {
+          e_carry = __shfl_sync(0xffffffffu, r_lo, 0) + NE;
+          if (e_carry >= __shfl_sync(0xffffffffu, r_hi, 0)) {  // exactly consumed
+            e_carry = -1;
+            n_cur += 1;
+          }
+        } else {
+          e_carry = -1;
+          n_cur += m;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_go[ms]);
+      ++k_sched;
+    };
+    MT_TC_TIMER();  // 0: wait for a free metadata slot, 1: schedule
+    while (!sched_done) {
+      // slot k_sched % 4 was last used by chunk k_sched - 4: wait until its consumers are done.  (A barrier of its own
+      // per slot: a parity wait is only defined for the current and the preceding phase, and empty[b] may already be
+      // two chunks further.)
+      const int K = k_sched;
+      if (K >= kTcMetaSlots) {
+        if (lane == 0) mbar_wait(&bar_mfree[K % kTcMetaSlots], ((K / kTcMetaSlots) - 1) & 1, 14);
+        __syncwarp();
+      }
+      MT_TACC(0);
+      schedule();
+      MT_TACC(1);
+    }
+    MT_TC_TIMER_FLUSH();
+  } else if (warp == kTcMmaWarp) {
+    // ================================================================ MMA issue (one thread; ~200 cycles per MMA: the
+    // operands travel through the uniform datapath -- a warp of its own keeps that off everybody's critical path)
+    const uint32_t idesc = make_idesc_bf16(128, NE);
+    const uint32_t a_lbo = (uint32_t)a_rows * 16, b_lbo = (uint32_t)NE * 16;
+    const uint32_t a_plane32 = (uint32_t)L.a_plane, b_plane32 = (uint32_t)L.b_plane;
+    const uint64_t a_desc0 = make_kmajor_desc(smem_u32(sA), a_lbo, 128);
+    const uint64_t b_desc0 = make_kmajor_desc(smem_u32(sB), b_lbo, 128);
+    MT_TC_TIMER();  // 0: wait go, 1: wait bready, 2: issue
+    for (int k = 0;; ++k) {
+      const int b = k & 1, ms = k % kTcMetaSlots;
+      const TcMeta& M = *reinterpret_cast<const TcMeta*>(sMeta + ms * kMetaBytes);
+      int nn = 0, nc = 0;
+      if (lane == 0) {
+        mbar_wait(&bar_go[ms], (k / kTcMetaSlots) & 1, 30 + ms);
+        nn = M.nnodes;
+        nc = M.ncols;
+      }
+      nn = __shfl_sync(0xffffffffu, nn, 0);
+      nc = __shfl_sync(0xffffffffu, nc, 0);
+      MT_TACC(0);
+      if (lane == 0) {
+        if (nn < 0) {
+          mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);  // the arrival belongs to chunk k's phase of full[b]
           mbar_arrive(&bar_full[b]);
+        } else {
+          // every chunk has one bready[b] phase (all MLP warps arrive, also for chunks without edges)
+          mbar_wait(&bar_bready[b], (k >> 1) & 1, 32 + b);
+          if (nc == 0) {
+            mbar_arrive(&bar_full[b]);  // no MMA for this chunk: plain arrival
+          } else {
+            tc_fence_after();
+            // significant products of (hi+mid+lo) x (hi+mid+lo), small ones first: planes (a, b) = (0,2) (2,0) (1,1)
+            // (0,1) (1,0) (0,0), two bits each, packed (a local array would live in local memory)
+            constexpr uint32_t kPa = 0u | (2u << 2) | (1u << 4) | (0u << 6) | (1u << 8) | (0u << 10);
+            constexpr uint32_t kPb = 2u | (0u << 2) | (1u << 4) | (1u << 6) | (0u << 8) | (0u << 10);
+            for (int t = 0; t < MT; ++t) {
+              const uint32_t d = tmem_base + (uint32_t)((b * MT + t) * NE);
+              uint32_t accum = 0;
+#pragma unroll
+              for (int q = 0; q < 6; ++q) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  // descriptors differ only in the start-address field (units of 16 bytes, no carry: < 2^14)
+                  const uint32_t a_off = ((kPa >> (2 * q)) & 3u) * a_plane32 + (uint32_t)(2 * ks) * a_lbo + (uint32_t)t * 128 * 16;
+                  const uint32_t b_off = ((kPb >> (2 * q)) & 3u) * b_plane32 + (uint32_t)(2 * ks) * b_lbo;
+                  umma_bf16(d, a_desc0 + (uint64_t)(a_off >> 4), b_desc0 + (uint64_t)(b_off >> 4), idesc, accum);
+                  accum = 1;
+                }
+              }
+            }
+            umma_commit(&bar_full[b]);
+            umma_commit(&bar_bfree);
+          }
+        }
+      }
+      __syncwarp();
+      MT_TACC(2);
+      if (nn < 0) break;
+    }
+    MT_TC_TIMER_FLUSH();
+  } else if (warp >= kTcFirstMlpWarp) {
+    // ================================================================ radial MLP
+    const int pw = warp - kTcFirstMlpWarp;
+    const int in0 = p.sizes[0];
+    const int q4 = lane & 3, cl = lane >> 2;      // four lanes per column: lane q4 produces outputs 8 q4 .. 8 q4 + 7
+    const int yn = p.y_dim;
+    const int yq = (yn + 3) >> 2;                 // sh components per lane: [q4 * yq, min(yn, (q4 + 1) * yq))
+    float* vrow = reinterpret_cast<float*>(smem + L.v_off) + (pw * 8 + cl) * 33;  // (kTcMlpWarps rows of 8 x 33 floats)
+    int n_mma = 0;  // chunks that carried edges so far
+    const CUtensorMap* map = &maps.m[part_id];
+    const uint32_t xrow_bytes = (uint32_t)P.x_cols * 4;
+    MT_TC_TIMER();  // 0: wait go, 1: loads, 2: hidden layers, 3: wait empty / bfree, 4: stores + gathers, 5: claim, 6: fence + arrive + MMA
+    for (int k = 0;; ++k) {
+      const int b = k & 1, ms = k % kTcMetaSlots;
+      TcMeta& M = *reinterpret_cast<TcMeta*>(sMeta + ms * kMetaBytes);
+      const int* cole = sColE + ms * 3 * NE;
+      const int* csrc = cole + NE;
+      const int* corig = cole + 2 * NE;
+      if (lane == 0) mbar_wait(&bar_go[ms], (k / kTcMetaSlots) & 1, 50 + ms);
+      __syncwarp();
+      MT_TACC(0);
+      const int nn = M.nnodes, ncols = M.ncols;
+      if (nn < 0) {
+        if (lane == 0) {  // terminator: every share of full[b] (the first MT warps also the MMA commit's)
+          mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);
           mbar_arrive(&bar_full[b]);
         }
         break;
       }
-      // ---- candidates: lane l looks at node n_cur + l (one coalesced rowptr read)
-      const int64_t cand = n_cur + lane;
-      const bool in_range = lane < kTcMaxNodes && cand < n_end;
-      int r_lo = in_range ? p.rowptr[cand] : 0;
-      const int r_hi = in_range ? p.rowptr[cand + 1] : 0;
-      if (lane == 0 && e_carry >= 0) r_lo = e_carry;
-      int deg = r_hi - r_lo;
-      bool split = false;
-      if (lane == 0 && deg > NE) {  // node larger than a chunk: take 64 edges now, the rest next time
-        deg = NE;
-        split = true;
-      }
-      const int degp = (deg + 3) & ~3;
-      int cum = in_range ? degp : 0x10000;  // inclusive prefix of padded degrees
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, cum, o);
-        if (lane >= o) cum += t;
-      }
-      const unsigned fm = __ballot_sync(0xffffffffu, in_range && cum <= NE);
-      int m = (fm == 0xffffffffu) ? 32 : (__ffs(~fm) - 1);  // leading run of nodes that fit
-      const bool split0 = __shfl_sync(0xffffffffu, (int)split, 0) != 0;
-      if (split0) m = 1;
-      const bool mine = lane < m;
-      const int cb = cum - degp;
-      const float den = mine ? (p.num_neigh ? sqrtf(p.num_neigh[cand]) : sqrtf(p.avg)) : 0.f;
-      const int ncols = __shfl_sync(0xffffffffu, cum, m - 1);
-      const int my_edges = mine ? deg : 0;
-      int tot_edges = my_edges;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tot_edges += __shfl_xor_sync(0xffffffffu, tot_edges, o);
-      // unpadded and consecutive in the sorted edge list (always, for whole nodes): the chunk's columns are ONE
-      // contiguous edge range -> one copy per plane segment instead of one per node
-      const bool contiguous = (ncols == tot_edges);
-      const int r_first = __shfl_sync(0xffffffffu, r_lo, 0);
-      MT_TACC(t_meta);
-      // ---- everything above only read global memory; now wait until the consumers released buffer b
-      if (lane == 0) mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);
-      MT_DBG(1000 + k * 10 + 1);
-      __syncwarp();
-      MT_TACC(t_we);
-      if (mine) {
-        M.node_id[lane] = (int)cand;
-        M.cb[lane] = (short)cb;
-        M.ngrp[lane] = (short)(degp >> 2);
-        M.first[lane] = (lane == 0 && e_carry >= 0) ? 0 : 1;
-        M.den[lane] = den;
-        M.rlo[lane] = r_lo;
-        M.deg[lane] = deg;
-      }
-      const bool continues = (e_carry >= 0);
-      if (lane == 0) {
-        M.nnodes = m;
-        M.ncols = ncols;
-        // a chunk that continues a node split over chunks accumulates into its output row: keep the pieces
-        // ordered (deterministic sum) by letting the previous chunk drain first
-        if (continues && k > 0) mbar_wait(&bar_empty[b ^ 1], ((k - 1) >> 1) & 1, 12);
-      }
-      __syncwarp();
-      float* xs = reinterpret_cast<float*>(smem + L.x_off + (size_t)b * L.x_buf);
+      const int nblk = (ncols + 7) >> 3;
+      bool waited = false;
+      uint32_t tx_bytes = 0;
       float* ys = reinterpret_cast<float*>(smem + L.y_off + (size_t)b * L.y_buf);
-      if (ncols == 0) {
-        if (lane == 0) {
-          s_cnt[b][0] = 0; s_cnt[b][1] = 0; s_cnt[b][2] = 0; s_cnt[b][3] = 0;
-          mbar_arrive(&bar_go[b]);
-          mbar_arrive(&bar_full[b]);  // nothing to copy, no MMA: both arrivals from here
-          mbar_arrive(&bar_full[b]);
-        }
-      } else {
-        if (lane == 0) {
-          s_cnt[b][0] = 0; s_cnt[b][1] = 0; s_cnt[b][2] = 0; s_cnt[b][3] = 0;
-          if (b_uses > 0) mbar_wait(&bar_bfree, (b_uses - 1) & 1, 21);  // previous MMAs have consumed the h planes
-        }
-        __syncwarp();
-        MT_TACC(t_wb);
-        MT_DBG(1000 + k * 10 + 2);
-        // pad rows of the h planes must be zero (zero weights for pad columns)
-        for (int j = 0; j < (contiguous ? 0 : m); ++j) {
-          const int dj = __shfl_sync(0xffffffffu, deg, j), cj = __shfl_sync(0xffffffffu, cb, j);
-          const int npad = ((dj + 3) & ~3) - dj;
-          for (int t = lane; t < npad * 12; t += 32) {
-            const int r = t / 12, pg = t - r * 12;
-            *reinterpret_cast<uint4*>(sB + (size_t)(pg >> 2) * L.b_plane + (size_t)(pg & 3) * NE * 16 +
-                                      (size_t)(cj + dj + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          s_mma_b = b;
-          mbar_arrive_expect_tx(&bar_full[b], (uint32_t)tot_edges * (xrow_bytes + yrow_bytes));
-          mbar_arrive_expect_tx(&bar_bready, (uint32_t)tot_edges * 16u * 12u);
-          mbar_arrive(&bar_go[b]);  // warps 2-3 issue the gathered x rows (one bulk copy per edge) from here
-        }
-        __syncwarp();
-        MT_TACC(t_pad);
-        MT_DBG(1000 + k * 10 + 3);
-        // bulk copies: 12 plane segments + the sh rows per node (contiguous: sorted order) -- or per chunk when the
-        // chunk's columns are one contiguous edge range; the x rows (one per edge) are issued by warps 2-3
-        if (contiguous) {
-          if (lane < 12) {
-            const int pl = lane >> 2, g = lane & 3;
-            bulk_g2s(sB + (size_t)pl * L.b_plane + (size_t)g * NE * 16,
-                     reinterpret_cast<const unsigned char*>(p.hplanes) + ((size_t)(pl * 4 + g) * p.E + r_first) * 16,
-                     (uint32_t)tot_edges * 16u, &bar_bready);
-          } else if (lane == 12) {
-            bulk_g2s(ys, p.ysorted + (size_t)r_first * p.y_pad, (uint32_t)tot_edges * yrow_bytes, &bar_full[b]);
-          }
-        }
-        for (int j = 0; j < (contiguous ? 0 : m); ++j) {
-          const int dj = __shfl_sync(0xffffffffu, deg, j), cj = __shfl_sync(0xffffffffu, cb, j);
-          const int rj = __shfl_sync(0xffffffffu, r_lo, j);
-          if (dj == 0) continue;
-          if (lane < 12) {
-            const int pl = lane >> 2, g = lane & 3;
-            bulk_g2s(sB + (size_t)pl * L.b_plane + (size_t)g * NE * 16 + (size_t)cj * 16,
-                     reinterpret_cast<const unsigned char*>(p.hplanes) + ((size_t)(pl * 4 + g) * p.E + rj) * 16,
-                     (uint32_t)dj * 16u, &bar_bready);
-          } else if (lane == 12) {
-            bulk_g2s(ys + (size_t)cj * p.y_pad, p.ysorted + (size_t)rj * p.y_pad, (uint32_t)dj * yrow_bytes,
-                     &bar_full[b]);
-          }
-        }
-        ++b_uses;
-        ++n_chunks;
-        MT_TACC(t_issue);
-        MT_DBG(1000 + k * 10 + 4);
-      }
-      // advance
-      if (split0) {
-        e_carry = __shfl_sync(0xffffffffu, r_lo, 0) + NE;
-        if (e_carry >= __shfl_sync(0xffffffffu, r_hi, 0)) {  // exactly consumed
-          e_carry = -1;
-          n_cur += 1;
-        }
-      } else {
-        e_carry = -1;
-        n_cur += m;
-      }
-    }
-    MT_TIMING_ONLY(if (p.dbg && blockIdx.x == 0 && lane == 0) {
-      p.dbg[8192 + 0] = t_we; p.dbg[8192 + 1] = t_meta; p.dbg[8192 + 2] = t_wb; p.dbg[8192 + 3] = t_pad;
-      p.dbg[8192 + 4] = t_issue; p.dbg[8192 + 6] = n_chunks;
-    })
-    (void)n_chunks;
-  } else if (warp == 2 || warp == 3) {
-    // ================================================================ gathered x rows: one bulk copy per edge
-    // (a UBLKCP is issued lane by lane, ~100 cycles each: two warps on two schedulers halve the issue time)
-    const int part = warp - 2;
-    const uint32_t xrow_bytes = (uint32_t)p.x_dim * 4;
-    MT_TIMING_ONLY(long long _tl = clock64(), t_wg = 0, t_cp = 0;)
-    for (int k = 0;; ++k) {
-      const int b = k & 1;
-      const TcMeta& M = b ? *meta1 : *meta0;
-      if (lane == 0) mbar_wait(&bar_go[b], (k >> 1) & 1, 50 + b);
-      __syncwarp();
-      MT_TACC(t_wg);
-      const int nn = M.nnodes;
-      if (nn < 0) break;
-      if (M.ncols > 0) {
-        float* xs = reinterpret_cast<float*>(smem + L.x_off + (size_t)b * L.x_buf);
-        for (int j = 0; j < nn; ++j) {
-          const int dj = M.deg[j], cj = M.cb[j], rj = M.rlo[j];
-          for (int e = 2 * lane + part; e < dj; e += 64)
-            bulk_g2s(xs + (size_t)(cj + e) * p.x_dim, p.x + (size_t)p.src[rj + e] * p.x_dim, xrow_bytes, &bar_full[b]);
-        }
-      }
-      MT_TACC(t_cp);
-    }
-    MT_TIMING_ONLY(if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 10 + 2 * part] = t_wg; p.dbg[8192 + 11 + 2 * part] = t_cp; })
-  } else if (warp == 1) {
-    // ================================================================ MMA issuer
-    const uint32_t idesc = make_idesc_bf16(128, NE);
-    const uint32_t a_lbo = (uint32_t)MT * 128 * 16, b_lbo = (uint32_t)NE * 16;
-    const uint64_t a_desc0 = make_kmajor_desc(smem_u32(sA), a_lbo, 128);
-    const uint64_t b_desc0 = make_kmajor_desc(smem_u32(sB), b_lbo, 128);
-    MT_TIMING_ONLY(long long _tl = clock64(), t_wr = 0, t_mma = 0;)
-    for (int k = 0;; ++k) {  // k counts the chunks that carry edges (and the terminator)
-      MT_DBG(2000 + k * 10 + 0);
-      // lane 0 alone reads the hand-over word: by the time the other lanes get here the producer may already
-      // have posted the next chunk (or the terminator) -- a per-lane read would split the warp
-      int b = 0;
-      if (lane == 0) {
-        mbar_wait(&bar_bready, k & 1, 30);
-        b = s_mma_b;
-      }
-      b = __shfl_sync(0xffffffffu, b, 0);
-      MT_DBG(2000 + k * 10 + 1);
-      MT_TACC(t_wr);
-      if (b < 0) break;
-      if (lane == 0) {
-        tc_fence_after();
-        // significant products of (hi+mid+lo) x (hi+mid+lo), small ones first
-        const int pa[6] = {0, 2, 1, 0, 1, 0};
-        const int pb[6] = {2, 0, 1, 1, 0, 0};
-        for (int t = 0; t < MT; ++t) {
-          const uint32_t d = tmem_base + (uint32_t)((b * MT + t) * NE);
-          uint32_t accum = 0;
+      while (true) {
+        int blk = 0;
+        if (lane == 0) blk = atomicAdd(&M.blk_next, 1);
+        blk = __shfl_sync(0xffffffffu, blk, 0);
+        if (blk >= nblk) break;
+        // ---------------- loads + hidden layers of the block's 8 columns (registers and the scratch row only)
+        const int c = 8 * blk + cl;
+        const int ce = (c < ncols) ? cole[c] : -1;
+        const bool real = ce >= 0;
+        const int e = real ? ce : (ce <= -2 ? (-2 - ce) : -1);  // pad column: operands of the node's last edge
+        const bool any = e >= 0;
+        float yv[7];
+        const float* er = p.emb;
+        if (any) {
+          const int64_t orig = corig[c];
+          const float* __restrict__ yr = p.sh + orig * yn;
 #pragma unroll
-          for (int q = 0; q < 6; ++q) {
+          for (int i = 0; i < 7; ++i) {
+            const int j = q4 * yq + i;
+            yv[i] = (i < yq && j < yn) ? yr[j] : 0.f;
+          }
+          er += orig * in0;
+        }
+        __syncwarp();  // the previous block of this warp has been stored
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              // descriptors differ only in the start-address field (units of 16 bytes, no carry: < 2^14)
-              const uint32_t a_off = (uint32_t)(pa[q] * L.a_plane) + (uint32_t)(2 * ks) * a_lbo + (uint32_t)t * 128 * 16;
-              const uint32_t b_off = (uint32_t)(pb[q] * L.b_plane) + (uint32_t)(2 * ks) * b_lbo;
-              umma_bf16(d, a_desc0 + (uint64_t)(a_off >> 4), b_desc0 + (uint64_t)(b_off >> 4), idesc, accum);
-              accum = 1;
+        for (int i = 0; i < 8; ++i) {
+          const int idx = 8 * q4 + i;
+          vrow[idx] = (real && idx < in0) ? er[idx] : 0.f;
+        }
+        __syncwarp();
+        MT_TACC(1);
+#pragma unroll 1
+        for (int li = 0; li < nh; ++li) {
+          const int K = p.sizes[li], fo = p.sizes[li + 1];
+          const float* W = sW + (li ? wrow1 : 0) * kTcK + 8 * q4;
+          float2 a[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = make_float2(0.f, 0.f);
+#pragma unroll 8
+          for (int kk = 0; kk < K; ++kk) {
+            const float hk = vrow[kk];
+            const float4* wr = reinterpret_cast<const float4*>(W + kk * kTcK);
+            const float4 w0 = wr[0], w1 = wr[1];
+            fma_pair(hk, w0.x, w0.y, a[0]);
+            fma_pair(hk, w0.z, w0.w, a[1]);
+            fma_pair(hk, w1.x, w1.y, a[2]);
+            fma_pair(hk, w1.z, w1.w, a[3]);
+          }
+          __syncwarp();  // all four lanes of the column have read the inputs
+          float o8[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            o8[2 * i] = a[i].x;
+            o8[2 * i + 1] = a[i].y;
+          }
+          if (p.act == MT_ACT_SILU) {  // the eight chains are independent: the special-function unit pipelines them
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o8[i] = o8[i] * tc_fast_sigmoid(o8[i]);
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) o8[i] = apply_act<float>(p.act, o8[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vrow[8 * q4 + i] = (8 * q4 + i < fo) ? o8[i] * p.act_cst : 0.f;
+          __syncwarp();
+        }
+        MT_TACC(2);
+        // ---------------- the stage must be free (consumers of chunk k - 2), and the MMAs of the previous chunk must
+        // have consumed the h planes before they are overwritten
+        if (!waited) {
+          if (lane == 0) {
+            mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);
+            if (n_mma > 0) mbar_wait(&bar_bfree, (n_mma - 1) & 1, 52);
+          }
+          __syncwarp();
+          waited = true;
+        }
+        MT_TACC(3);
+        // the block's sender rows: two TMA gathers of 4 rows (sender rows resolved by the scheduler)
+        if (lane < 2 && 8 * blk + 4 * lane < ncols) {
+          const int g = 2 * blk + lane;
+          const int4 r = *reinterpret_cast<const int4*>(csrc + 4 * g);
+          tma_gather4(smem + L.x_off + (size_t)b * L.x_buf + (size_t)(4 * g) * xrow_bytes, map, P.x_lo, r.x, r.y, r.z, r.w,
+                      &bar_full[b]);
+        }
+        tx_bytes += 4 * xrow_bytes * (uint32_t)((8 * blk < ncols) + (8 * blk + 4 < ncols));
+        if (any) {
+          // sh components -> pair-interleaved padded row: degree-l block at position sh_pad_pos(l)
+          float* yo = ys + (size_t)(c >> 1) * ystride + (c & 1);
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const int j = q4 * yq + i;
+            if (i < yq && j < yn) {
+              const int l = (j >= 16) ? 4 : (j >= 9) ? 3 : (j >= 4) ? 2 : (j >= 1) ? 1 : 0;
+              yo[2 * (sh_pad_pos(l) + j - l * l)] = yv[i];
             }
           }
         }
-        umma_commit(&bar_full[b]);
-        umma_commit(&bar_bfree);
+        if (c < ncols) {
+          float h8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h8[i] = real ? vrow[8 * q4 + i] : 0.f;  // pad column: zero weights
+          uint4 hi, mi, lo;
+          tc_split8(h8, hi, mi, lo);
+          unsigned char* dst = sB + (size_t)q4 * NE * 16 + (size_t)c * 16;  // k-group q4 of the column
+          *reinterpret_cast<uint4*>(dst) = hi;
+          *reinterpret_cast<uint4*>(dst + L.b_plane) = mi;
+          *reinterpret_cast<uint4*>(dst + 2 * L.b_plane) = lo;
+        }
+        MT_TACC(4);
+      }
+      if (!waited && lane == 0) mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);  // arrivals belong to chunk k's phase
+      MT_TACC(5);
+      if (pw == 0 && lane == 0) {
+        s_cnt[b][0] = 0; s_cnt[b][1] = 0; s_cnt[b][2] = 0; s_cnt[b][3] = 0;
+        // a chunk that continues a node split over chunks accumulates into its output row: keep the pieces
+        // ordered (deterministic sum) by letting the previous chunk drain first
+        if (M.continues && k > 0) mbar_wait(&bar_empty[b ^ 1], ((k - 1) >> 1) & 1, 12);
+      }
+      if (ncols > 0) fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bar_bready[b]);
+        // this warp's sh rows of the chunk and the bytes of the gathers it issued
+        if (tx_bytes) mbar_arrive_expect_tx(&bar_full[b], tx_bytes);
+        else mbar_arrive(&bar_full[b]);
       }
       __syncwarp();
-      MT_TACC(t_mma);
-      MT_DBG(2000 + k * 10 + 2);
+      if (ncols > 0) ++n_mma;
+      MT_TACC(6);
     }
-    MT_TIMING_ONLY(if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 8] = t_wr; p.dbg[8192 + 9] = t_mma; })
-  } else if (warp >= kTcProducerWarps) {
+    MT_TC_TIMER_FLUSH();
+  } else {
     // ================================================================ consumers
     const int q = warp & 3;
-    const int nsubq = p.q_count[q];
-    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
-    MT_TIMING_ONLY(long long _tl = clock64(), t_wf = 0, t_work = 0;)
+    const int nbiq = P.q_count[q];
+    MT_TC_TIMER();  // 0: wait full, 1: units, 7: units processed
     for (int k = 0;; ++k) {
       const int b = k & 1;
-      MT_DBG(3000 + k * 100 + 0);
-      mbar_wait(&bar_full[b], (k >> 1) & 1, 40 + b);
-      MT_TACC(t_wf);
-      MT_DBG(3000 + k * 100 + 1);
+      // one lane waits (a warp-wide poll would flood the shared-memory pipe the producers' LDS need)
+      if (lane == 0) mbar_wait(&bar_full[b], (k >> 1) & 1, 40 + b);
+      __syncwarp();
+      MT_TACC(0);
       tc_fence_after();
-      const TcMeta& M = b ? *meta1 : *meta0;
+      const TcMeta& M = *reinterpret_cast<const TcMeta*>(sMeta + (k % kTcMetaSlots) * kMetaBytes);
       const int nn = M.nnodes;
       if (nn < 0) break;
-      const float* xs = reinterpret_cast<const float*>(smem + L.x_off + (size_t)b * L.x_buf);
-      const float* ys = reinterpret_cast<const float*>(smem + L.y_off + (size_t)b * L.y_buf);
-      const int num_units = nsubq * nn;
+      TcUnit u;
+      u.tstage = tmem_base + (uint32_t)(b * MT * NE);
+      u.quarter = q;
+      u.ne = NE;
+      u.xs = reinterpret_cast<const float*>(smem + L.x_off + (size_t)b * L.x_buf);
+      u.xstride = P.x_cols;
+      u.ys = reinterpret_cast<const float*>(smem + L.y_off + (size_t)b * L.y_buf);
+      u.ystride = ystride;
+      const int num_units = nbiq * nn;
       while (true) {
         int unit = 0;
         if (lane == 0) unit = atomicAdd(&s_cnt[b][q], 1);
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= num_units) break;
         const int si = unit / nn, nj = unit - si * nn;
-        const int sub = sQ[q * kTcMaxSub + si];
-        MT_DBG(3000 + k * 100 + 10 + unit);
-        const uint32_t hd = sHdr[sub];
-        const int type = hd & 0xff, cpw = (hd >> 8) & 0xff, lane0 = (hd >> 16) & 0xff, tile = (hd >> 24) & 15;
-        const int d3 = hd >> 28;
-        const TcSlot slot = sSlot[sub * 32 + lane];
-        const int cb = M.cb[nj], ngrp = M.ngrp[nj];
-        MT_TIMING_ONLY(const long long u0 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;)
-        float acc[kTcD];
-#pragma unroll
-        for (int m = 0; m < kTcD; ++m) acc[m] = 0.f;
+        const int bi = sQ[q * kTcMaxBI + si];
+        const int4 h0 = *reinterpret_cast<const int4*>(sHdr + bi * 8);
+        const int4 h1 = *reinterpret_cast<const int4*>(sHdr + bi * 8 + 4);
+        u.mask = (unsigned)h0.w;
+        u.nch = h0.z;
+        u.slot[0] = h1.y; u.slot[1] = h1.z; u.slot[2] = h1.w;
+        u.lt = sLane[bi * 32 + lane];
+        u.cb = M.cb[nj];
+        u.ngrp = M.ngrp[nj];
+        u.out = p.out + (size_t)M.node_id[nj] * p.out_dim;
+        u.inv_den = M.inv_den[nj];
+        u.first = M.first[nj] != 0;
         __syncwarp();
-        if (ngrp > 0) {
-          const uint32_t taddr = tmem_base + lane_base + (uint32_t)((b * MT + tile) * NE + cb);
-          const float* xp = xs + (size_t)cb * p.x_dim + slot.xoff;
-          const float* yp = ys + (size_t)cb * p.y_pad + slot.yoff;
-          const int src_lane = (lane0 + (lane & (cpw - 1))) & 31;
-          switch (type) {
-#define MT_TC_CASE(ID, A, B, C)                                                           \
-  case ID:                                                                                \
-    tc_unit<A, B, C>(taddr, xp, p.x_dim, yp, p.y_pad, ngrp, cpw, lane, src_lane, acc);    \
+        switch (h0.x) {
+#define MT_TC_CASE(ID) \
+  case ID:             \
+    tc_unit_dispatch<ID>(u, h0.y, lane); \
     break;
-            MT_FOR_EACH_CG_TYPE_L2(MT_TC_CASE)
+          MT_FOR_EACH_BUNDLE_L2(MT_TC_CASE)
+          default:
+            if constexpr (LMAXK > 2) {
+              switch (h0.x) {
+                MT_FOR_EACH_BUNDLE_GT2(MT_TC_CASE)
+                default: break;
+              }
+            }
+            break;
 #undef MT_TC_CASE
-            default: break;
-          }
         }
-        for (int off = cpw; off < 32; off <<= 1) {
-#pragma unroll
-          for (int m = 0; m < kTcD; ++m) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], off);
-        }
-        MT_TIMING_ONLY(if (p.dbg && blockIdx.x == 0 && lane == 0) {
-          atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg) + 8192 + 128 + sub, (unsigned long long)(clock64() - u0));
-          atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg) + 8192 + 256 + sub, 1ull);
-        })
-        if (slot.valid && lane < cpw) {
-          float* o = p.out + (size_t)M.node_id[nj] * p.out_dim + slot.ooff;
-          const float den = M.den[nj];
-          // `first` is warp-uniform; keep the accumulate case apart so the common case issues no loads
-          if (M.first[nj]) {
-#pragma unroll
-            for (int m = 0; m < kTcD; ++m)
-              if (m < d3) o[m] = acc[m] / den;
-          } else {
-#pragma unroll
-            for (int m = 0; m < kTcD; ++m)
-              if (m < d3) o[m] += acc[m] / den;
-          }
-        }
+        __syncwarp();
+        if (_tm) _ta[7] += 16;
       }
-      MT_DBG(3000 + k * 100 + 90);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_empty[b]);
-      MT_TACC(t_work);
+      if (lane == 0) {
+        mbar_arrive(&bar_empty[b]);
+        mbar_arrive(&bar_mfree[k % kTcMetaSlots]);
+      }
+      MT_TACC(1);
     }
-    MT_TIMING_ONLY(if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8192 + 16 + 2 * warp] = t_wf; p.dbg[8192 + 17 + 2 * warp] = t_work; })
+    MT_TC_TIMER_FLUSH();
   }
   // ---------------------------------------------------------------- teardown
-  MT_DBG(9000);
   tc_fence_before();
   __syncthreads();
-  MT_DBG_BLOCK(1);
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc(tmem_base, tmem_cols);
+    tmem_dealloc(tmem_base, 512);
   }
-  MT_DBG_BLOCK(2);
 }
 
 }  // namespace mt

@@ -214,20 +214,36 @@ class ConvPlanHandle:
             s.mlp_sizes[i] = int(v)
         s.mlp_act = int(act_id)
         s.mlp_act_cst = float(act_cst)
-        s.tc_num_tiles = 0
-        if getattr(uvu_plan, "tc_num_tiles", 0) > 0:
-            self.tc_tables = [t.to(device).contiguous() for t in (uvu_plan.tc_row_wcol, uvu_plan.tc_sub_hdr,
-                                                                   uvu_plan.tc_sub_slot, uvu_plan.tc_q_list)]
-            s.tc_num_tiles = uvu_plan.tc_num_tiles
-            s.tc_num_sub = uvu_plan.tc_num_sub
-            s.tc_row_wcol, s.tc_sub_hdr, s.tc_sub_slot, s.tc_q_list = [t.data_ptr() for t in self.tc_tables]
-            for q in range(4):
-                s.tc_q_count[q] = uvu_plan.tc_q_count[q]
+        s.tc_num_parts = 0
+        tc = getattr(uvu_plan, "tc", None)
+        self.tc_tables = []
+        if tc is not None and tc.parts:
+            s.tc_num_parts = len(tc.parts)
+            s.tc_y_lmax = tc.y_lmax
+            for i, part in enumerate(tc.parts):
+                tabs = [t.to(device).contiguous() for t in (part.row_wcol, part.bi_hdr, part.bi_lane, part.q_list)]
+                self.tc_tables.append(tabs)
+                ps = s.tc_parts[i]
+                ps.num_tiles, ps.a_rows, ps.num_bi = part.num_tiles, part.a_rows, len(part.bis)
+                ps.x_lo, ps.x_cols, ps.lmax = part.x_lo, part.x_cols, part.lmax
+                ps.cost = max(1, int(round(part.cost)))
+                for q in range(4):
+                    ps.q_count[q] = part.q_count[q]
+                ps.row_wcol, ps.bi_hdr, ps.bi_lane, ps.q_list = [t.data_ptr() for t in tabs]
         self.bw_tables = [t.to(device).contiguous() for t in (uvu_plan.bw_item_hdr, uvu_plan.bw_lane_tab,
                                                                uvu_plan.bw_path_tab)]
         s.bw_num_items, s.bw_num_paths = uvu_plan.bw_num_items, uvu_plan.bw_num_paths
         s.bw_item_hdr, s.bw_lane_tab, s.bw_path_tab = [t.data_ptr() for t in self.bw_tables]
         self.struct = s
+        # the tensor-core forward gathers sender rows with TMA: rows must be multiples of 16 bytes.  Layers whose
+        # feature row is not (the lmax-4 layers: 214 / 246 floats) run on a zero-padded copy of x with a padded plan.
+        self.x_pad = (-uvu_plan.x_dim) % 4 if s.tc_num_parts > 0 else 0
+        self.struct_fwd = s
+        if self.x_pad:
+            s2 = ConvPlanStruct()
+            C.memmove(C.byref(s2), C.byref(s), C.sizeof(ConvPlanStruct))
+            s2.x_dim = uvu_plan.x_dim + self.x_pad
+            self.struct_fwd = s2
         self.mlp_sizes = list(mlp_sizes)
         self.device = torch.device(device)
 
@@ -251,19 +267,32 @@ def conv_fwd(handle: ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Ten
     if num_neigh is not None:
         num_neigh = _req(num_neigh, "num_neigh", x.dtype)
     out = torch.empty((N, pl.out_dim), dtype=x.dtype, device=x.device)
-    ws_bytes = lib.mt_conv_fwd_workspace_bytes(C.byref(handle.struct), _dt(x), N, E)
+    st = handle.struct
+    if handle.x_pad and x.dtype == torch.float32:
+        x = torch.nn.functional.pad(x, (0, handle.x_pad))
+        st = handle.struct_fwd
+    ws_bytes = lib.mt_conv_fwd_workspace_bytes(C.byref(st), _dt(x), N, E)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     if CONV_EVENTS is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         ev0.record()
-    check(lib.mt_conv_fwd(C.byref(handle.struct), _dt(x), _p(x), _p(sh), _p(emb), wptrs, _p(rowptr), _p(perm),
+    check(lib.mt_conv_fwd(C.byref(st), _dt(x), _p(x), _p(sh), _p(emb), wptrs, _p(rowptr), _p(perm),
                           _p(src_sorted), float(avg_num_neighbors) if avg_num_neighbors is not None else 0.0,
                           _p(num_neigh), _p(out), _p(ws), ws_bytes, N, E, _stream(x)))
     if CONV_EVENTS is not None:
         ev1.record()
         CONV_EVENTS.append(((pl.x_dim, pl.y_dim, pl.out_dim, pl.weight_numel, N, E), ev0, ev1))
     return out
+
+
+_IMPLS = {"auto": 0, "tc": 1, "fma": 2}
+
+
+def conv_select_impl(name: str) -> str:
+    """Selects the fp32 kernel of conv_fwd ('auto' | 'tc' | 'fma'); returns the previous selection."""
+    old = _lib.load().mt_conv_select_impl(_IMPLS[name])
+    return {v: k for k, v in _IMPLS.items()}[old]
 
 
 def conv_bwd(handle: ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Tensor], rowptr, perm, src_sorted,

@@ -11,7 +11,6 @@ Init-time planners: turn irreps into the flat tables the CUDA kernels consume.
 from __future__ import annotations
 
 import math
-import os
 from dataclasses import dataclass
 from typing import Dict, List, Tuple
 
@@ -108,111 +107,15 @@ class UVUPlan:
         self.slot_tab = torch.tensor([t[3] for t in items], dtype=torch.int32).reshape(self.num_items, 32, 4)
 
     def _build_tc(self):
-        """Tables of the tcgen05 path (csrc/conv_fwd_tc.cuh).  Weight columns become rows of the MMA A
-        operand in groups of 32 TMEM lanes (one warp "quarter" of a 128-row tile).  A type's columns are cut
-        into full groups of 32 (one sub-item, lane == row) plus a remainder that is padded to cpw = 8 or 16
-        lanes and packed with other small remainders into shared groups; a packed sub-item runs on all 32
-        lanes as (column, edge-phase) pairs.  Groups are spread over the 4 quarters to balance their cost."""
-        self.tc_num_tiles = 0
-        if max(max(p.l1, p.l2, p.l3) for p in self.paths) > 2:
-            return  # the tensor-core kernel instantiates the l <= 2 contractions only
-        by_type = {}
-        for p in self.paths:
-            cols = by_type.setdefault((p.l1, p.l2, p.l3), [])
-            for u in range(p.mul):
-                cols.append((p.w_off + u, p.x_off + u * (2 * p.l1 + 1), p.y_off, p.out_off + u * (2 * p.l3 + 1)))
-        subs = []  # dict(type, cpw, cols, cost)
-        # A (sub-item, node) unit is one dependent chain on one warp, and a chunk holds only ~2 nodes, so the
-        # slowest unit of a chunk sets its duration.  Heavy types are therefore cut into sub-items of 16 or 8
-        # columns (cpw): such a sub-item runs its columns on 32/cpw edge phases, i.e. 32/cpw times shorter.
-        # Cost model: measured cycles per (sub-item, node) unit of the bench graph (tools/tc_debug.py, r1): a
-        # lane == row unit costs 3.5 + 0.28 nnz + 0.35 (D1 + D2 - 2) kcycles; a packed (cpw 8 / 16) unit is NOT
-        # cheaper than a full one (5.3 + 0.145 nnz): its columns x edge phases keep all 32 lanes busy for as many
-        # iterations.  Splitting full types into packed ones (MT_TC_UNIT_COST < 100) therefore does not pay.
-        unit_cost = float(os.environ.get("MT_TC_UNIT_COST", "100"))
-        for (l1, l2, l3), cols in by_type.items():
-            nnz = cg_nnz(l1, l2, l3)
-            full = 3.5 + 0.28 * nnz + 0.35 * (2 * l1 + 2 * l2)
-            packed = 5.3 + 0.145 * nnz
-            for c0 in range(0, len(cols), 32):
-                chunk = cols[c0:c0 + 32]
-                cpw = 32 if len(chunk) > 16 else (16 if len(chunk) > 8 else 8)
-                while cpw > 8 and full * cpw / 32.0 > unit_cost:
-                    cpw //= 2
-                for s0 in range(0, len(chunk), cpw):
-                    subs.append({"type": cg_type_id(l1, l2, l3), "cpw": cpw, "cols": chunk[s0:s0 + cpw],
-                                 "cost": full if cpw == 32 else packed, "d3": 2 * l3 + 1})
-        # pack: cpw == 32 sub-items own a group of 32 TMEM lanes; smaller ones share groups.  A packed sub-item
-        # costs as much as a full one, so the packed ones are spread over as many groups as the tile count
-        # leaves free (longest-processing-time first), not squeezed into the fewest.
-        groups = []  # dict(subs=[(sub index, lane0)], used=lanes)
-        for i, sb in enumerate(subs):
-            if sb["cpw"] == 32:
-                groups.append({"subs": [(i, 0)], "used": 32})
-        small = sorted([i for i, sb in enumerate(subs) if sb["cpw"] < 32], key=lambda i: -subs[i]["cost"])
-        n_full = len(groups)
-        lanes_small = sum(subs[i]["cpw"] for i in small)
-        MT = (n_full + (lanes_small + 31) // 32 + 3) // 4
-        packed = [{"subs": [], "used": 0, "cost": 0.0} for _ in range(max(4 * MT - n_full, 0))] if small else []
-        for i in small:
-            fits = [g for g in packed if g["used"] + subs[i]["cpw"] <= 32]
-            if not fits:  # fragmentation: one more group (MT is recomputed below)
-                packed.append({"subs": [], "used": 0, "cost": 0.0})
-                fits = [packed[-1]]
-            g = min(fits, key=lambda g: g["cost"])
-            g["subs"].append((i, g["used"]))
-            g["used"] += subs[i]["cpw"]
-            g["cost"] += subs[i]["cost"]
-        groups += [g for g in packed if g["subs"]]
-        MT = (len(groups) + 3) // 4
-        self.tc_num_tiles = 0
-        if MT > 4 or len(subs) > 64:
-            return  # does not fit 512 TMEM rows: the FMA-pipe kernel handles this plan
-        for g in groups:
-            g["cost"] = sum(subs[i]["cost"] for i, _ in g["subs"])
-        groups.sort(key=lambda g: -g["cost"])
-        qcost, qn = [0.0] * 4, [0] * 4
-        row_wcol = [-1] * (MT * 128)
-        hdr = [[0] * 8 for _ in subs]
-        slot = [[[0, 0, 0, 0] for _ in range(32)] for _ in subs]
-        qlist = [[] for _ in range(4)]
-        # quarters <-> warp schedulers: the 7 consumer warps of quarter q share scheduler q and its instruction
-        # cache, so besides balancing the cost, keep the number of DISTINCT contraction types per quarter small
-        # (ncu r1: instruction fetch was the top stall of the 64-column kernels)
-        type_penalty = float(os.environ.get("MT_TC_TYPE_PENALTY", "2.0"))
-        qtypes = [set() for _ in range(4)]
-        for g in groups:
-            gt = {(subs[i]["type"], subs[i]["cpw"] == 32) for i, _ in g["subs"]}  # (type, loop variant) = code
-            q = min((q for q in range(4) if qn[q] < MT),
-                    key=lambda q: qcost[q] + type_penalty * len(gt - qtypes[q]))
-            qtypes[q] |= gt
-            t = qn[q]
-            qn[q] += 1
-            qcost[q] += g["cost"]
-            for i, lane0 in g["subs"]:
-                sb = subs[i]
-                hdr[i] = [sb["type"], sb["cpw"], lane0, t, q, sb["d3"], 0, 0]
-                for j, (wc, xo, yo, oo) in enumerate(sb["cols"]):
-                    row_wcol[t * 128 + q * 32 + lane0 + j] = wc
-                for lane in range(32):
-                    j = lane % sb["cpw"]
-                    if j < len(sb["cols"]):
-                        _, xo, yo, oo = sb["cols"][j]
-                        slot[i][lane] = [xo, yo, oo, 1]
-                qlist[q].append(i)
-        for q in range(4):
-            qlist[q].sort(key=lambda i: -subs[i]["cost"])
-        self.tc_num_tiles = MT
-        self.tc_num_sub = len(subs)
-        self.tc_row_wcol = torch.tensor(row_wcol, dtype=torch.int32)
-        self.tc_sub_hdr = torch.tensor(hdr, dtype=torch.int32)
-        self.tc_sub_slot = torch.tensor(slot, dtype=torch.int32)
-        ql = torch.zeros((4, 64), dtype=torch.int32)
-        for q in range(4):
-            ql[q, :len(qlist[q])] = torch.tensor(qlist[q], dtype=torch.int32)
-        self.tc_q_list = ql
-        self.tc_q_count = [len(qlist[q]) for q in range(4)]
-        self.tc_q_cost = qcost
+        """Tables of the tcgen05 path (csrc/conv_fwd_tc.cuh): see matten_b200/tcplan.py."""
+        from .tcplan import TCPlan
+
+        self.tc = TCPlan(self)
+
+    @property
+    def tc_num_tiles(self) -> int:
+        """Total MMA tiles of the tcgen05 plan (0: the plan runs on the FMA-pipe kernel)."""
+        return sum(p.num_tiles for p in self.tc.parts)
 
     def _build_bwd(self):
         """Tables of the backward kernel (csrc/conv_bwd.cuh).  The backward is organised by INPUT channel:

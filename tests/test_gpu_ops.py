@@ -346,17 +346,13 @@ def test_conv_mlp_variants(dev, dtype):
 
 # ------------------------------------------------------------------ tcgen05 path of the convolution
 def _with_impl(impl, fn):
-    import os
+    from matten_b200 import ops
 
-    old = os.environ.get("MT_CONV_IMPL")
-    os.environ["MT_CONV_IMPL"] = impl
+    old = ops.conv_select_impl(impl)
     try:
         return fn()
     finally:
-        if old is None:
-            del os.environ["MT_CONV_IMPL"]
-        else:
-            os.environ["MT_CONV_IMPL"] = old
+        ops.conv_select_impl(old)
 
 
 @pytest.mark.parametrize("impl", ["tc", "fma"])
@@ -381,7 +377,7 @@ def test_conv_tensor_core_and_fma_paths(dev, impl):
                    lambda n: n % 40, 17)
 
     _with_impl(impl, run)
-    # row length not a multiple of 4 floats (no 16-byte bulk copies): automatic fallback to the FMA kernel
+    # row length not a multiple of 4 floats (TMA rows are multiples of 16 bytes): automatic fallback to the FMA kernel
     _with_impl("auto", lambda: _conv_case(dev, f32, "20x0e+12x1o+5x2e+3x1e", 2, "20x0e+12x1o+5x2e+3x1e", 2, 8, 16, 2,
                                           9.0, 60, lambda n: n % 30, 20))
     # three hidden layers: the tensor-core path keeps at most two in registers -> automatic fallback

@@ -169,53 +169,72 @@ def test_backward_tables_cover_every_channel_and_weight_column_once(x_ir, sh_lma
     assert out_seen == [1] * pl.out_dim
 
 
-@pytest.mark.parametrize("x_ir,out_ir", [
-    ("16x0e", "52x0e+16x1o+4x2e"),
-    ("32x0e+16x1o+4x2e", "72x0e+16x1o+16x1e+4x2o+4x2e"),
-    ("32x0o+32x0e+16x1o+16x1e+4x2o+4x2e", "32x0o+32x0e+16x1o+16x1e+4x2o+4x2e"),
-    ("20x0e+12x1o+4x2e+4x1e", "20x0e+12x1o+4x2e+4x1e"),
-    ("32x0e+32x1o+32x2e", "32x0e+32x1o+32x2e"),
+@pytest.mark.parametrize("x_ir,out_ir,lmax", [
+    ("16x0e", "52x0e+16x1o+4x2e", 2),
+    ("32x0e+16x1o+4x2e", "72x0e+16x1o+16x1e+4x2o+4x2e", 2),
+    ("32x0o+32x0e+16x1o+16x1e+4x2o+4x2e", "32x0o+32x0e+16x1o+16x1e+4x2o+4x2e", 2),
+    ("20x0e+12x1o+4x2e+4x1e", "20x0e+12x1o+4x2e+4x1e", 2),
+    ("32x0e+32x1o+32x2e", "32x0e+32x1o+32x2e", 2),
+    ("32x0o+32x0e+16x1o+16x1e+4x2o+4x2e+2x3o+2x3e+4x4e", "32x0o+32x0e+16x1o+16x1e+4x2o+4x2e+2x3o+2x3e+4x4e", 4),
+    ("8x0e+8x1o+8x2e+8x3o+8x4e", "8x0e+8x1o+8x2e+8x3o+8x4e", 4),
 ])
-def test_tcgen05_tables_place_every_weight_column_on_one_tmem_lane(x_ir, out_ir):
-    """Tables of the tensor-core path (plan._build_tc): every weight column of the tensor product sits on exactly one
-    row of the MMA A operand (= one TMEM lane of one tile); a sub-item's lanes read the rows of its own 32-lane
-    quarter; every quarter holds at most num_tiles groups; the slot tables address the same x / sh / out elements as
-    the forward items of the FMA-pipe kernel."""
+def test_tcgen05_tables_reproduce_the_tensor_product(x_ir, out_ir, lmax):
+    """Tables of the tensor-core path (matten_b200/tcplan.py): every weight column sits on a row of the MMA A operand
+    (= one TMEM lane of one tile; duplicated only over the edge-phase row blocks of mode P), all rows of a bundle
+    instance lie in its own 32-lane quarter, no slot is used twice -- and a host emulation of the kernel's indexing
+    (rows -> lanes, lane tables, path masks, per-part x windows) reproduces the dense uvu tensor product of the
+    oracle for one edge, every output element written exactly once."""
     from matten_b200 import o3
+    from matten_b200.codegen.gen_bundles import bundle_menu
     from matten_b200.plan import UVUPlan
+    from matten_b200.tcplan import MAX_TILES, emulate
+    from oracle import e3nn_restated as E
 
-    pl = UVUPlan(o3.Irreps(x_ir), o3.Irreps.spherical_harmonics(2), o3.Irreps(out_ir))
-    assert 1 <= pl.tc_num_tiles <= 4
-    rows = pl.tc_row_wcol.tolist()
-    assert len(rows) == pl.tc_num_tiles * 128
-    used = sorted(r for r in rows if r >= 0)
-    assert used == list(range(pl.weight_numel))  # each weight column exactly once
-    ref = {}
-    for (tid, cpw), slots in zip(pl.item_hdr.tolist(), pl.slot_tab.tolist()):
-        for wcol, xoff, yoff, ooff in slots:
-            if wcol >= 0:
-                ref[wcol] = (tid, xoff, yoff, ooff)
-    hdr, slot = pl.tc_sub_hdr.tolist(), pl.tc_sub_slot.tolist()
-    per_q_tiles = [set() for _ in range(4)]
-    seen = set()
-    for (tid, cpw, lane0, tile, q, d3, _, _), sl in zip(hdr, slot):
-        assert cpw in (8, 16, 32) and 0 <= lane0 and lane0 + cpw <= 32 and 0 <= tile < pl.tc_num_tiles
-        per_q_tiles[q].add(tile)
-        for j in range(cpw):
-            xoff, yoff, ooff, valid = sl[j]
-            wcol = rows[tile * 128 + q * 32 + lane0 + j]
-            assert (wcol >= 0) == bool(valid)
-            if valid:
-                assert ref[wcol] == (tid, xoff, yoff, ooff)
-                assert wcol not in seen
-                seen.add(wcol)
-        for lane in range(cpw, 32):  # further edge phases repeat the columns
-            assert sl[lane] == sl[lane % cpw]
-    assert len(seen) == pl.weight_numel
-    assert all(len(t) <= pl.tc_num_tiles for t in per_q_tiles)
-    assert sum(pl.tc_q_count) == pl.tc_num_sub
-    ql = pl.tc_q_list.tolist()
-    listed = sorted(s for q in range(4) for s in ql[q][:pl.tc_q_count[q]])
-    assert listed == list(range(pl.tc_num_sub))
-    for q in range(4):
-        assert all(hdr[s][4] == q for s in ql[q][:pl.tc_q_count[q]])
+    pl = UVUPlan(o3.Irreps(x_ir), o3.Irreps.spherical_harmonics(lmax), o3.Irreps(out_ir))
+    tc = pl.tc
+    assert tc.parts, "plan must qualify for the tensor-core path"
+    menu = bundle_menu()
+    seen_cols = set()
+    for part in tc.parts:
+        assert 1 <= part.num_tiles <= MAX_TILES and part.x_lo % 4 == 0 and part.x_cols % 8 == 0
+        rows = part.row_wcol.tolist()
+        assert len(rows) == part.num_tiles * 128
+        owner = {}
+        for k, (bid, mode, nch, mask, q, s0, s1, s2) in enumerate(part.bi_hdr.tolist()):
+            b = menu[bid]
+            assert mode in (0, 1) and nch in ((32,) if mode == 0 else (8, 4, 2)) and 0 <= q < 4 and mask
+            for p_i in range(len(b.paths)):
+                if not (mask >> p_i) & 1:
+                    continue
+                s = (s0, s1, s2)[p_i]
+                tile, half = s // 2, s % 2
+                assert 0 <= tile < part.num_tiles
+                lanes = range(32) if mode == 0 else range(16 * half + 8 * (p_i % 2), 16 * half + 8 * (p_i % 2) + 8)
+                for ln in lanes:
+                    key = (tile, q, ln)
+                    assert key not in owner, "two paths share a TMEM lane"
+                    owner[key] = (k, p_i)
+                if mode == 1:  # duplicate row blocks hold the same weight column
+                    base = tile * 128 + 32 * q + 16 * half + 8 * (p_i % 2)
+                    for r8 in range(8):
+                        assert rows[base + r8] == rows[base + r8 % nch]
+        for r, wc in enumerate(rows):
+            if wc >= 0:
+                assert (r // 128, (r % 128) // 32, r % 32) in owner
+                seen_cols.add(wc)
+        assert sum(part.q_count) == part.bi_hdr.shape[0]
+        ql = part.q_list.tolist()
+        listed = sorted(s for q in range(4) for s in ql[q][:part.q_count[q]])
+        assert listed == list(range(part.bi_hdr.shape[0]))
+    assert seen_cols == set(range(pl.weight_numel))
+    # one edge through the tables vs the oracle's dense tensor product
+    torch.manual_seed(1)
+    x = torch.randn(pl.x_dim, dtype=torch.float64)
+    y = torch.randn(pl.y_dim, dtype=torch.float64)
+    w = torch.randn(pl.weight_numel, dtype=torch.float64)
+    got = emulate(tc, pl, x, y, w)
+    instr = [(p.i_in1, p.i_in2, p.i_out, "uvu", True) for p in pl.paths]
+    tp = E.TensorProduct(str(pl.irreps_in1), str(pl.irreps_in2), str(pl.irreps_mid), instr,
+                         shared_weights=False, internal_weights=False).double()
+    want = tp(x[None], y[None], w[None])[0]
+    assert torch.allclose(got, want, rtol=0, atol=1e-12), float((got - want).abs().max())
