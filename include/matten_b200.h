@@ -239,8 +239,10 @@ typedef struct {
  *   (sum_{e: dst(e)=n} msg_e) / sqrt(avg_num_neighbors)        if num_neigh == NULL
  *   (sum ...)             / sqrt(num_neigh[n])                  otherwise (reference
  *   src/matten/nn/conv.py:116-120). Summation order is the CSR order: deterministic. */
-/* workspace (bytes): 0 for every current kernel (the tcgen05 path evaluates the hidden layers of the radial MLP
- * inside the fused kernel); kept in the ABI so that a caller never has to change when a kernel needs scratch. */
+/* workspace (bytes) of the tcgen05 path: the receiver-sorted edge list in padded column order (every node's edges
+ * padded to a multiple of 4 columns: original edge id and sender row per column), the last hidden activation of the
+ * radial MLP as bf16 hi/mid/lo planes (192 B per column) and pair-interleaved sh rows.  0 when the plan / dtype runs
+ * on the FMA-pipe kernel, which needs none. */
 size_t mt_conv_fwd_workspace_bytes(const mt_conv_plan* plan, int dtype, int64_t N, int64_t E);
 int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* sh,
                 const void* emb, const void* const* mlp_weights, const int32_t* rowptr,

@@ -18,7 +18,7 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
                     const void* const* mlp_weights, const int32_t* rowptr, const int32_t* perm,
                     const int32_t* src_sorted, double avg, const void* num_neigh, void* out, void* workspace,
                     size_t workspace_bytes, int64_t N, int64_t E, cudaStream_t st, int* used);
-size_t conv_fwd_tc_workspace_bytes(const mt_conv_plan* plan, int64_t E);
+size_t conv_fwd_tc_workspace_bytes(const mt_conv_plan* plan, int64_t N, int64_t E);
 void conv_fwd_tc_set_debug(void* p);
 
 // Tuning overrides (MT_CONV_*) are read from the environment ONCE per process: nothing on the call path touches getenv.
@@ -157,9 +157,8 @@ int mt_conv_select_impl(int impl) {
 }
 
 size_t mt_conv_fwd_workspace_bytes(const mt_conv_plan* plan, int dtype, int64_t N, int64_t E) {
-  (void)N;
-  if (plan == nullptr || dtype != MT_F32) return 0;
-  return conv_fwd_tc_workspace_bytes(plan, E);
+  if (plan == nullptr || dtype != MT_F32 || conv_env().impl == 2) return 0;
+  return conv_fwd_tc_workspace_bytes(plan, N, E);
 }
 
 int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* sh, const void* emb,

@@ -1,6 +1,8 @@
 // Host launcher of the tcgen05 convolution forward (see conv_fwd_tc.cuh).
 #include <stdlib.h>
 
+#include <cub/device/device_scan.cuh>
+
 #include "conv_fwd_tc.cuh"
 
 namespace mt {
@@ -8,17 +10,12 @@ namespace mt {
 constexpr size_t kTcSmemLimit = (size_t)227 * 1024 - 1024;  // dynamic + static shared memory must fit 227 KB
 
 // widest chunk (MMA N, a multiple of 16) whose staging buffers fit the shared memory; 0: none
-static int tc_w_rows(const mt_conv_plan* plan) {
-  const int nh = plan->mlp_num_layers - 1;
-  return (nh > 0 ? tc_pad8(plan->mlp_sizes[0]) : 0) + (nh > 1 ? tc_pad8(plan->mlp_sizes[1]) : 0);
-}
-
-static int tc_pick_ne(const mt_conv_tc_part& part, int y_lmax, int w_rows) {
+static int tc_pick_ne(const mt_conv_tc_part& part, int y_lmax) {
   static const int cand[] = {256, 128, 80, 64, 48, 32};
   const int y_pad = sh_pad_len(y_lmax);
   for (int ne : cand) {
     if (2 * part.num_tiles * ne > 512) continue;
-    const TcSmemLayout L = tc_smem_layout(part.a_rows, part.x_cols, y_pad, part.num_bi, ne, w_rows);
+    const TcSmemLayout L = tc_smem_layout(part.a_rows, part.x_cols, y_pad, part.num_bi, ne);
     if (L.total <= kTcSmemLimit) return ne;
   }
   return 0;
@@ -37,12 +34,46 @@ static bool tc_plan_qualifies(const mt_conv_plan* plan) {
     if (pt.a_rows <= 0 || pt.a_rows > pt.num_tiles * 128 || (pt.a_rows & 31) != 0) return false;
     if (!pt.row_wcol || !pt.bi_hdr || !pt.bi_lane || !pt.q_list) return false;
     if (pt.x_cols <= 0 || pt.x_cols > 256 || (pt.x_cols & 7) != 0 || (pt.x_lo & 3) != 0) return false;
-    if (tc_pick_ne(pt, plan->tc_y_lmax, tc_w_rows(plan)) == 0) return false;
+    if (tc_pick_ne(pt, plan->tc_y_lmax) == 0) return false;
   }
   return true;
 }
 
-size_t conv_fwd_tc_workspace_bytes(const mt_conv_plan*, int64_t) { return 0; }
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// workspace: the padded column order of the receiver-sorted edge list and what the fused kernel streams per column
+struct TcWorkspace {
+  size_t rowptr_pad, scan_tmp, orig_pad, src_pad, hplanes, ypairs, total;
+  int64_t cols_max;
+  size_t scan_bytes;
+};
+static TcWorkspace tc_workspace(const mt_conv_plan* plan, int64_t N, int64_t E) {
+  TcWorkspace w;
+  w.cols_max = (E + 3 * N + 3) & ~(int64_t)3;
+  if (w.cols_max < 4) w.cols_max = 4;
+  w.scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, w.scan_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)(N + 1));
+  size_t o = 0;
+  w.rowptr_pad = o;
+  o += align256((size_t)(N + 1) * 4 * 2);  // padded degrees, then their scan
+  w.scan_tmp = o;
+  o += align256(w.scan_bytes);
+  w.orig_pad = o;
+  o += align256((size_t)w.cols_max * 4);
+  w.src_pad = o;
+  o += align256((size_t)w.cols_max * 4);
+  w.hplanes = o;
+  o += align256((size_t)w.cols_max * 192);
+  w.ypairs = o;
+  o += align256((size_t)(w.cols_max / 2) * 2 * sh_pad_len(plan->tc_y_lmax) * 4);
+  w.total = o + 256;
+  return w;
+}
+
+size_t conv_fwd_tc_workspace_bytes(const mt_conv_plan* plan, int64_t N, int64_t E) {
+  if (!tc_plan_qualifies(plan) || N <= 0) return 0;
+  return tc_workspace(plan, N, E).total;
+}
 
 static long long* g_tc_dbg = nullptr;  // phase-timing buffer of the next launches (mt_conv_set_debug_buffer)
 void conv_fwd_tc_set_debug(void* p) { g_tc_dbg = static_cast<long long*>(p); }
@@ -71,11 +102,11 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
                     const void* const* mlp_weights, const int32_t* rowptr, const int32_t* perm,
                     const int32_t* src_sorted, double avg, const void* num_neigh, void* out, void* workspace,
                     size_t workspace_bytes, int64_t N, int64_t E, cudaStream_t st, int* used) {
-  (void)workspace;
-  (void)workspace_bytes;
   *used = 0;
   if (!tc_plan_qualifies(plan)) return MT_OK;
-  if (E >= (int64_t)2147483647 || N >= (int64_t)2147483647) return MT_OK;
+  if (E + 3 * N >= (int64_t)2147483647 || N >= (int64_t)2147483647) return MT_OK;
+  const TcWorkspace W = tc_workspace(plan, N, E);
+  if (workspace == nullptr || workspace_bytes < W.total) return MT_OK;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return MT_OK;
   EncodeTiledFn encode = encode_tiled_fn();
   if (encode == nullptr) return set_error(MT_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -102,6 +133,38 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
   p.E = E;
   p.num_parts = plan->tc_num_parts;
   p.dbg = g_tc_dbg;
+  {
+    const uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+    int32_t* degp = reinterpret_cast<int32_t*>(base + W.rowptr_pad);
+    p.rowptr_pad = degp + (N + 1);
+    p.orig_pad = reinterpret_cast<int32_t*>(base + W.orig_pad);
+    p.src_pad = reinterpret_cast<int32_t*>(base + W.src_pad);
+    p.hplanes = reinterpret_cast<__nv_bfloat16*>(base + W.hplanes);
+    p.ypairs = reinterpret_cast<float*>(base + W.ypairs);
+    p.cols_max = W.cols_max;
+    // (1) padded column order
+    tc_pad_degree_kernel<<<(unsigned)ceil_div<int64_t>(N + 1, 256), 256, 0, st>>>(rowptr, N, degp);
+    MT_LAUNCH_OK();
+    size_t scan_bytes = W.scan_bytes;
+    MT_CUDA_OK(cub::DeviceScan::ExclusiveSum(reinterpret_cast<void*>(base + W.scan_tmp), scan_bytes, degp, p.rowptr_pad,
+                                             (int)(N + 1), st));
+    count_launch();
+    {
+      int64_t g = ceil_div<int64_t>(N * 32, 256);
+      if (g > (int64_t)kNumSMs * 32) g = (int64_t)kNumSMs * 32;
+      if (g < 1) g = 1;
+      tc_pad_layout_kernel<<<(unsigned)g, 256, 0, st>>>(rowptr, p.rowptr_pad, perm, src_sorted, N, p.orig_pad, p.src_pad);
+      MT_LAUNCH_OK();
+    }
+    // (2) hidden layers of the radial MLP + sh pair rows, per padded column
+    {
+      int64_t g = ceil_div<int64_t>(W.cols_max, 64);
+      if (g > (int64_t)kNumSMs * 8) g = (int64_t)kNumSMs * 8;
+      if (g < 1) g = 1;
+      tc_edge_hidden_kernel<<<(unsigned)g, kHidThreads, 0, st>>>(p);
+      MT_LAUNCH_OK();
+    }
+  }
   // CTAs per part follow the part's cost (every part walks all edges; heavy parts get more SMs)
   int64_t grid = kNumSMs;
   if (grid > N * p.num_parts) grid = N * p.num_parts;
@@ -121,7 +184,7 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
     q.num_bi = pt.num_bi;
     q.x_lo = pt.x_lo;
     q.x_cols = pt.x_cols;
-    q.ne = tc_pick_ne(pt, plan->tc_y_lmax, tc_w_rows(plan));
+    q.ne = tc_pick_ne(pt, plan->tc_y_lmax);
     for (int k = 0; k < 4; ++k) q.q_count[k] = pt.q_count[k];
     q.row_wcol = pt.row_wcol;
     q.bi_hdr = pt.bi_hdr;
@@ -137,7 +200,7 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
     q.cta_count = n;
     assigned += n;
     if (pt.lmax > lmax) lmax = pt.lmax;
-    const TcSmemLayout L = tc_smem_layout(q.a_rows, q.x_cols, sh_pad_len(p.y_lmax), q.num_bi, q.ne, tc_w_rows(plan));
+    const TcSmemLayout L = tc_smem_layout(q.a_rows, q.x_cols, sh_pad_len(p.y_lmax), q.num_bi, q.ne);
     if (L.total > smem_max) smem_max = L.total;
     // x as a 2D tensor [N][x_dim] of fp32, box {x_cols, 1}: tile::gather4 fetches 4 arbitrary rows per instruction
     cuuint64_t dims[2] = {(cuuint64_t)plan->x_dim, (cuuint64_t)(N > 0 ? N : 1)};

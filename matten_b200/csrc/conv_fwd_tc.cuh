@@ -1,6 +1,5 @@
 // Fused convolution forward, Blackwell-native version (fp32 storage):
 //
-//   hidden layers of the radial MLP  h = act(act(emb W1) W2)      -> FP32 FMA pipes, dedicated warps, lane == edge
 //   last radial-MLP layer            w[e, c] = sum_k h[e,k] W[k,c] -> tcgen05.mma (bf16 x3 split, fp32 accumulate)
 //   accumulators                                                   -> TMEM  (lane = weight column c, column = edge e)
 //   gathered sender rows x[src]                                    -> TMA tile::gather4 (4 rows per instruction)
@@ -8,31 +7,33 @@
 //                                                                     operands in shared memory, per-node sums in
 //                                                                     registers (CSR order, no atomics)
 //
-// Same contract as conv_fwd.cuh (reference src/matten/nn/utils.py:260-263 + src/matten/nn/conv.py:113-120): neither
-// the hidden activations, nor the per-edge tensor-product weights [E, weight_numel], nor the messages [E, D_mid]
-// ever leave the SM.  One launch per call, no workspace.
+// Same contract as conv_fwd.cuh (reference src/matten/nn/utils.py:260-263 + src/matten/nn/conv.py:113-120): the
+// per-edge tensor-product weights [E, weight_numel] and the messages [E, D_mid] never leave the SM.
 //
-// One CTA per SM, persistent over a contiguous node range (balanced by edge count), 20 warps = 5 per scheduler:
-//   warps 0..11   consumers.  Warp w reads TMEM lanes 32 (w % 4) .. .  Work units (bundle instance, node) are handed
-//                 out dynamically per quarter.  A bundle instance (matten_b200/tcplan.py) is a group of input channels
-//                 x a compile-time list of paths that share the loads of x[u, :] and Y (generated/cg_bundles.cuh):
-//                   mode L: lane == channel (32 channels), the warp walks the node's edge pairs;
-//                   mode P: 8 / 4 / 2 channels x edge phases through the tcgen05.ld.16x256b fragment
-//                           (thread 4 r + ph: TMEM rows r and r + 8, column pair ph of 4).
-//   warps 12..18  radial MLP.  Blocks of 8 chunk columns are claimed dynamically; four lanes own a column: they load
-//                 the edge's radial embedding and spherical harmonics, evaluate the hidden layers (8 outputs per lane,
-//                 layer inputs exchanged through a shared-memory row), write h as three bf16 planes (the B operand)
-//                 and the harmonics as pair-interleaved rows.  They compute ahead of the buffers: only the stores
-//                 wait for the consumers.
-//   warp 19       control: scheduler (node-aligned chunks: every node's edges padded to a multiple of 4 columns,
-//                 <= NE columns, published up to 3 chunks ahead), TMA gathers of the chunk's sender rows, and the
-//                 chunk's tcgen05.mma's: D[t] (128 x NE, TMEM) = A[t] (128 rows of W^T, K = 32) x B^T (NE edges),
-//                 6 significant products of the 3 x 3 bf16 split (~2^-24).
-//   Single-warp code runs at ~10 cycles per instruction here (every instruction waits for the previous one, nothing
-//   else to issue): the radial MLP therefore needs several warps in flight, and the consumers as many as fit.
-//   Double buffered TMEM accumulators and x / Y staging; mbarriers: go[m] (chunk metadata published), bready[b] (h
-//   planes written), bfree (MMAs have read them), full[b] (gather bytes + Y rows + tcgen05.commit), empty[b]
-//   (consumers done with the stage).
+// Three kernels per call:
+//  (1) tc_pad_layout_kernel: the receiver-sorted edge list in PADDED column order -- every node's edges padded to a
+//      multiple of 4 columns (pad columns repeat the node's last edge and get zero weights): per column the original
+//      edge id and the sender row.  With this layout every chunk of the fused kernel is ONE contiguous column range.
+//  (2) tc_edge_hidden_kernel: the small hidden layers of the radial MLP (8 -> 32 -> 32) per column, four lanes per
+//      column, written as three bf16 planes (hi / mid / lo) in the K-major core-matrix layout the MMA wants (192 bytes
+//      per column), plus the edge's spherical harmonics as pair-interleaved padded rows.
+//      (Round 2 also built this stage INTO the fused kernel, on dedicated warps: correct, but slower -- a lone warp
+//      per scheduler runs such code at ~10 cycles per instruction and the h planes of the next chunk sat on the
+//      critical path; measurements in DESIGN.md.)
+//  (3) conv_fwd_tc_kernel: 1 CTA per SM, persistent over a contiguous node range (balanced by edge count), 18 warps:
+//        warp 0      builds node-aligned chunks (<= NE columns) and issues the copies of the chunk: 12 bulk copies of
+//                    the h planes, one of the sh rows, one TMA gather of 4 sender rows per 4 columns;
+//        warp 1      one thread issues the tcgen05.mma's of the chunk: D[t] (128 x NE, TMEM) = A[t] (128 rows of W^T,
+//                    K = 32) x B^T (NE columns), 6 significant products of the 3 x 3 bf16 split (~2^-24);
+//        warps 2..17 consumers.  Warp w reads TMEM lanes 32 (w % 4) .. .  Work units (bundle instance, node) are
+//                    handed out dynamically per quarter.  A bundle instance (matten_b200/tcplan.py) is a group of
+//                    input channels x a compile-time list of paths that share the loads of x[u, :] and Y
+//                    (generated/cg_bundles.cuh):
+//                      mode L: lane == channel (32 channels), the warp walks the node's edge pairs;
+//                      mode P: 8 / 4 / 2 channels x edge phases through the tcgen05.ld.16x256b fragment
+//                              (thread 4 r + ph: TMEM rows r and r + 8, column pair ph of 4).
+//      Double buffered TMEM accumulators and x / Y staging; mbarriers: full[b] (copy bytes + tcgen05.commit),
+//      empty[b] (consumers), bready / bfree (h planes landed / consumed by the MMAs).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -43,17 +44,13 @@
 namespace mt {
 
 constexpr int kTcK = 32;              // padded size of the last hidden layer == MMA K total
-constexpr int kTcConsumerWarps = 12;  // a multiple of 4: warp w reads TMEM quarter w % 4
-constexpr int kTcMlpWarps = 6;        // radial-MLP warps (+ the TMA gathers of their columns)
-constexpr int kTcFirstMlpWarp = kTcConsumerWarps;
-constexpr int kTcMmaWarp = kTcConsumerWarps + kTcMlpWarps;  // MMA issue
-constexpr int kTcControlWarp = kTcMmaWarp + 1;              // scheduler
-constexpr int kTcThreads = 32 * (kTcControlWarp + 1);       // 20 warps: 5 per scheduler, 96 registers per thread
+constexpr int kTcProducerWarps = 3;   // warp 0: chunks + plane / sh copies, warp 1: MMA issue, warp 2: TMA gathers
+constexpr int kTcConsumerWarps = 16;  // a multiple of 4: warp w reads TMEM quarter w % 4
+constexpr int kTcThreads = 32 * (kTcProducerWarps + kTcConsumerWarps);
 constexpr int kTcMaxTiles = 4;        // M tiles of 128 rows per part
 constexpr int kTcMaxBI = 64;          // bundle instances per part
 constexpr int kTcMaxNodes = 32;       // receiver nodes per chunk
 constexpr int kTcMaxParts = 4;
-constexpr int kTcMetaSlots = 4;       // chunk metadata ring: scheduler and MLP warps run ahead of the two stages
 
 // columns (padded edges) per chunk == MMA N: 2 stages x MT tiles x NE columns must fit the 512 TMEM columns
 __host__ __device__ constexpr int tc_chunk_cols(int MT) { return MT <= 1 ? 256 : (MT == 2 ? 128 : (MT == 3 ? 80 : 64)); }
@@ -84,6 +81,13 @@ struct ConvTcParams {
   const int32_t* rowptr;
   const int32_t* perm;
   const int32_t* src;
+  // padded column order (workspace, written by the two preparation kernels)
+  int32_t* rowptr_pad;        // [N+1] first padded column of every node (multiples of 4); [N] = number of columns
+  int32_t* orig_pad;          // [cols] original edge id of the column (pad column: -1 - id of the node's last edge)
+  int32_t* src_pad;           // [cols] sender row of the column
+  __nv_bfloat16* hplanes;     // [3][4][cols_max][8] bf16: plane, k-group, column, k % 8
+  float* ypairs;              // [cols_max / 2][2 * y_pad]: pair-interleaved padded sh rows
+  int64_t cols_max;           // allocated columns (E + 3 N rounded up to 4)
   float avg;
   const float* num_neigh;
   float* out;
@@ -205,6 +209,15 @@ __device__ __forceinline__ void tma_gather4(void* dst_smem, const CUtensorMap* m
       : "memory");
 }
 
+// bulk asynchronous copy global -> shared (the non-tensor TMA path); completes bytes on an mbarrier.
+// size and both addresses are multiples of 16 bytes.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // K-major, no-swizzle ("interleave") shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
 //   element (row r, k) of a [rows x 16] bf16 K-step lives at
 //   start + (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2   bytes
@@ -238,12 +251,11 @@ struct __align__(16) TcMeta {
   int nnodes;  // -1: terminate
   int ncols;   // used (padded) columns; 0: only nodes without edges
   int continues;  // 1: the first node of the chunk continues a node split over chunks
-  int pad1;
+  int pc0;        // first padded column of the chunk
   int node_id[kTcMaxNodes];
   float inv_den[kTcMaxNodes];        // 1 / sqrt(avg_num_neighbors) or 1 / sqrt(num_neigh[node])
   short cb[kTcMaxNodes];             // first column of the node (multiple of 4)
   short ngrp[kTcMaxNodes];           // padded edge count / 4
-  int blk_next;                      // next 8-column block of the chunk nobody has claimed yet (MLP warps)
   unsigned char first[kTcMaxNodes];  // 1: this chunk holds the node's first edges (plain store), 0: accumulate
 };
 
@@ -254,10 +266,7 @@ struct TcSmemLayout {
   size_t b_off, b_plane;  // 3 planes of [NE x 32] bf16
   size_t x_off, x_buf;    // 2 buffers [NE][x_cols] fp32
   size_t y_off, y_buf;    // 2 buffers [NE/2][2 * y_pad] fp32 (pair-interleaved sh rows)
-  size_t w_off;           // hidden-layer weights, pre-scaled: [w_rows][32] fp32 (layer 0 rows, then layer 1 rows)
-  size_t v_off;           // per MLP warp: [8 columns][33] fp32 layer inputs / outputs (stride 33: conflict-free)
-  size_t meta_off;        // kTcMetaSlots TcMeta
-  size_t cole_off;        // kTcMetaSlots x [3][NE] int per column: receiver-sorted edge (or pad marker), sender row, original edge
+  size_t meta_off;        // 2 TcMeta
   size_t lane_off;        // [num_bi][32] int4
   size_t hdr_off;         // [num_bi][8] int
   size_t qlist_off;       // [4][kTcMaxBI] uint8
@@ -265,7 +274,7 @@ struct TcSmemLayout {
 };
 __host__ __device__ inline size_t tc_align(size_t v, size_t a = 128) { return (v + a - 1) & ~(a - 1); }
 __host__ __device__ inline int tc_pad8(int v) { return (v + 7) & ~7; }
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int a_rows, int x_cols, int y_pad, int num_bi, int NE, int w_rows) {
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int a_rows, int x_cols, int y_pad, int num_bi, int NE) {
   TcSmemLayout L;
   size_t o = 0;
   L.a_off = o;
@@ -280,14 +289,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int a_rows, int x_cols, i
   L.y_off = o;
   L.y_buf = tc_align((size_t)(NE / 2) * 2 * y_pad * 4);
   o += 2 * L.y_buf;
-  L.w_off = o;
-  o = tc_align(o + (size_t)w_rows * kTcK * 4);
-  L.v_off = o;
-  o = tc_align(o + (size_t)kTcMlpWarps * 8 * 33 * 4);
   L.meta_off = o;
-  o = tc_align(o + kTcMetaSlots * tc_align(sizeof(TcMeta), 16));
-  L.cole_off = o;
-  o = tc_align(o + kTcMetaSlots * 3 * (size_t)NE * 4);
+  o = tc_align(o + 2 * tc_align(sizeof(TcMeta), 16));
   L.lane_off = o;
   o += (size_t)num_bi * 32 * 16;
   L.hdr_off = o;
@@ -491,7 +494,7 @@ __device__ __forceinline__ void tc_unit_dispatch(const TcUnit u, int mode, int l
 }
 
 // =====================================================================================================
-// radial MLP pieces (producer warps)
+// preparation kernels: padded column order, hidden layers of the radial MLP, sh pair rows
 // =====================================================================================================
 // sigmoid through the special-function unit: ex2.approx (2 ulp) and rcp.approx (1 ulp); relative error ~3e-7
 __device__ __forceinline__ float tc_fast_sigmoid(float v) {
@@ -521,10 +524,132 @@ __device__ __forceinline__ void tc_split8(const float (&v)[8], uint4& hi, uint4&
   mi = make_uint4(M[0], M[1], M[2], M[3]);
   lo = make_uint4(Lo[0], Lo[1], Lo[2], Lo[3]);
 }
-__device__ __forceinline__ float tc_act(int act, float v) {
-  if (act == MT_ACT_SILU) return v * tc_fast_sigmoid(v);
-  if (act == MT_ACT_SIGMOID) return tc_fast_sigmoid(v);
-  return apply_act<float>(act, v);
+
+// padded degrees (multiples of 4), to be scanned into rowptr_pad
+__global__ void __launch_bounds__(256) tc_pad_degree_kernel(const int32_t* __restrict__ rowptr, int64_t N,
+                                                            int32_t* __restrict__ degp) {
+  const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n < N) degp[n] = (rowptr[n + 1] - rowptr[n] + 3) & ~3;
+  if (n == N) degp[n] = 0;
+}
+
+// one warp per node: the node's padded columns
+__global__ void __launch_bounds__(256) tc_pad_layout_kernel(const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ rowptr_pad,
+                                                            const int32_t* __restrict__ perm, const int32_t* __restrict__ src,
+                                                            int64_t N, int32_t* __restrict__ orig_pad,
+                                                            int32_t* __restrict__ src_pad) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; n < N; n += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int r0 = rowptr[n], deg = rowptr[n + 1] - r0;
+    const int c0 = rowptr_pad[n], degp = rowptr_pad[n + 1] - c0;
+    for (int t = lane; t < degp; t += 32) {
+      const int e = r0 + (t < deg ? t : deg - 1);  // pad columns repeat the node's last edge
+      const int o = perm[e];
+      orig_pad[c0 + t] = (t < deg) ? o : (-1 - o);
+      src_pad[c0 + t] = src[e];
+    }
+  }
+}
+
+// hidden layers + sh pair rows: four lanes per column (lane q4 produces outputs 8 q4 .. 8 q4 + 7), 8 columns per warp
+// pass; layer inputs / outputs are exchanged through a shared-memory row per column (stride 33: conflict free)
+constexpr int kHidThreads = 256;
+__global__ void __launch_bounds__(kHidThreads) tc_edge_hidden_kernel(const ConvTcParams p) {
+  __shared__ __align__(16) float sW[2 * kTcK * kTcK];
+  __shared__ float sV[(kHidThreads / 32) * 8 * 33];
+  const int nh = p.nl - 1;
+  for (int li = 0; li < nh; ++li) {
+    const int fi = p.sizes[li], fo = p.sizes[li + 1];
+    const float s = rsqrtf((float)fi);
+    for (int t = threadIdx.x; t < kTcK * kTcK; t += kHidThreads) {
+      const int k = t >> 5, j = t & 31;
+      sW[li * kTcK * kTcK + t] = (k < fi && j < fo) ? p.w[li][(size_t)k * fo + j] * s : 0.f;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q4 = lane & 3, cl = lane >> 2;
+  const int in0 = p.sizes[0], yn = p.y_dim;
+  const int yq = (yn + 3) >> 2;  // sh components per lane: [q4 * yq, min(yn, (q4 + 1) * yq))
+  const int ystride = 2 * sh_pad_len(p.y_lmax);
+  float* vrow = sV + (warp * 8 + cl) * 33;
+  const int64_t cols = p.rowptr_pad[p.N];
+  uint4* planes = reinterpret_cast<uint4*>(p.hplanes);
+  const int64_t wpb = kHidThreads / 32;
+  for (int64_t c0 = (blockIdx.x * wpb + warp) * 8; c0 < cols; c0 += (int64_t)gridDim.x * wpb * 8) {
+    const int64_t c = c0 + cl;  // cols is a multiple of 4: a block of 8 may end half way
+    const bool in = c < cols;
+    const int oe = in ? p.orig_pad[c] : 0;
+    const bool real = in && oe >= 0;
+    const int64_t orig = oe >= 0 ? oe : (-1 - oe);
+    if (in) {
+      // sh components -> pair-interleaved padded row: degree-l block at position sh_pad_pos(l)
+      const float* __restrict__ yr = p.sh + orig * yn;
+      float* yo = p.ypairs + (c >> 1) * ystride + (c & 1);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const int j = q4 * yq + i;
+        if (i < yq && j < yn) {
+          const int l = (j >= 16) ? 4 : (j >= 9) ? 3 : (j >= 4) ? 2 : (j >= 1) ? 1 : 0;
+          yo[2 * (sh_pad_pos(l) + j - l * l)] = yr[j];
+        }
+      }
+    }
+    const float* er = p.emb + orig * in0;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = 8 * q4 + i;
+      vrow[idx] = (real && idx < in0) ? er[idx] : 0.f;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int li = 0; li < nh; ++li) {
+      const int K = p.sizes[li], fo = p.sizes[li + 1];
+      const float* W = sW + li * kTcK * kTcK + 8 * q4;
+      float2 a[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = make_float2(0.f, 0.f);
+#pragma unroll 8
+      for (int kk = 0; kk < K; ++kk) {
+        const float hk = vrow[kk];
+        const float4* wr = reinterpret_cast<const float4*>(W + kk * kTcK);
+        const float4 w0 = wr[0], w1 = wr[1];
+        fma_pair(hk, w0.x, w0.y, a[0]);
+        fma_pair(hk, w0.z, w0.w, a[1]);
+        fma_pair(hk, w1.x, w1.y, a[2]);
+        fma_pair(hk, w1.z, w1.w, a[3]);
+      }
+      __syncwarp();  // all four lanes of the column have read the inputs
+      float o8[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        o8[2 * i] = a[i].x;
+        o8[2 * i + 1] = a[i].y;
+      }
+      if (p.act == MT_ACT_SILU) {  // the eight chains are independent: the special-function unit pipelines them
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o8[i] = o8[i] * tc_fast_sigmoid(o8[i]);
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) o8[i] = apply_act<float>(p.act, o8[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vrow[8 * q4 + i] = (8 * q4 + i < fo) ? o8[i] * p.act_cst : 0.f;
+      __syncwarp();
+    }
+    if (in) {
+      float h8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h8[i] = real ? vrow[8 * q4 + i] : 0.f;  // pad column: zero weights
+      uint4 hi, mi, lo;
+      tc_split8(h8, hi, mi, lo);
+      planes[(size_t)(0 * 4 + q4) * p.cols_max + c] = hi;  // k-group q4 of the column
+      planes[(size_t)(1 * 4 + q4) * p.cols_max + c] = mi;
+      planes[(size_t)(2 * 4 + q4) * p.cols_max + c] = lo;
+    }
+  }
 }
 
 // =====================================================================================================
@@ -534,9 +659,10 @@ template <int LMAXK>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid_constant__ ConvTcParams p,
                                                                    const __grid_constant__ TcMaps maps) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar_full[2], bar_empty[2], bar_bready[2], bar_go[kTcMetaSlots], bar_mfree[kTcMetaSlots], bar_bfree;
+  __shared__ uint64_t bar_full[2], bar_empty[2], bar_go[2], bar_bready, bar_bfree;
   __shared__ uint32_t s_tmem_base;
   __shared__ int s_cnt[2][4];
+  __shared__ int s_mma_b;  // buffer of the chunk handed to the MMA warp (-1: terminate)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // which part does this CTA run, and which share of the node range
@@ -548,32 +674,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid
   const int MT = P.num_tiles, NE = P.ne, a_rows = P.a_rows;
   const int y_pad = sh_pad_len(p.y_lmax);
   const int ystride = 2 * y_pad;
-  const int nh = p.nl - 1;  // hidden layers (0 .. 2)
-  const int wrow1 = nh > 0 ? tc_pad8(p.sizes[0]) : 0;  // rows of layer 0 in sW; layer 1 follows
-  const int w_rows = wrow1 + (nh > 1 ? tc_pad8(p.sizes[1]) : 0);
-  const TcSmemLayout L = tc_smem_layout(a_rows, P.x_cols, y_pad, P.num_bi, NE, w_rows);
+  const TcSmemLayout L = tc_smem_layout(a_rows, P.x_cols, y_pad, P.num_bi, NE);
   unsigned char* sA = smem + L.a_off;
   unsigned char* sB = smem + L.b_off;
-  float* sW = reinterpret_cast<float*>(smem + L.w_off);
   unsigned char* sMeta = smem + L.meta_off;
   constexpr size_t kMetaBytes = (sizeof(TcMeta) + 15) & ~(size_t)15;
-  int* sColE = reinterpret_cast<int*>(smem + L.cole_off);
   int4* sLane = reinterpret_cast<int4*>(smem + L.lane_off);
   int* sHdr = reinterpret_cast<int*>(smem + L.hdr_off);
   unsigned char* sQ = smem + L.qlist_off;
 
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
-    mbar_init(&bar_full[0], kTcMlpWarps + 1);  // MLP warps (sh rows written, gather bytes) + the MMA commit
-    mbar_init(&bar_full[1], kTcMlpWarps + 1);
+    mbar_init(&bar_full[0], 2);  // producer (copy bytes) + MMA commit
+    mbar_init(&bar_full[1], 2);
     mbar_init(&bar_empty[0], kTcConsumerWarps);
     mbar_init(&bar_empty[1], kTcConsumerWarps);
-    mbar_init(&bar_bready[0], kTcMlpWarps);
-    mbar_init(&bar_bready[1], kTcMlpWarps);
-    for (int i = 0; i < kTcMetaSlots; ++i) {
-      mbar_init(&bar_go[i], 1);
-      mbar_init(&bar_mfree[i], kTcConsumerWarps);
-    }
+    mbar_init(&bar_go[0], 1);
+    mbar_init(&bar_go[1], 1);
+    mbar_init(&bar_bready, 1);
     mbar_init(&bar_bfree, 1);
     fence_barrier_init();
   }
@@ -582,20 +700,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid
   for (int t = tid; t < P.num_bi * 32; t += kTcThreads) sLane[t] = reinterpret_cast<const int4*>(P.bi_lane)[t];
   for (int t = tid; t < P.num_bi * 8; t += kTcThreads) sHdr[t] = P.bi_hdr[t];
   for (int t = tid; t < 4 * kTcMaxBI; t += kTcThreads) sQ[t] = (unsigned char)P.q_list[t];
-  // hidden-layer weights, pre-scaled by 1/sqrt(fan_in), rows padded to a multiple of 8, 32 (zero padded) columns
-  for (int li = 0; li < nh; ++li) {
-    const int fi = p.sizes[li], fo = p.sizes[li + 1];
-    const float s = rsqrtf((float)fi);
-    float* W = sW + (li ? wrow1 : 0) * kTcK;
-    for (int t = tid; t < tc_pad8(fi) * kTcK; t += kTcThreads) {
-      const int k = t >> 5, j = t & 31;
-      W[t] = (k < fi && j < fo) ? p.w[li][(size_t)k * fo + j] * s : 0.f;
-    }
-  }
-  // staging buffers start zeroed: pad columns / never-written pad positions are read and must hold finite values
+  // staging buffers start zeroed (columns past the chunk's range are never read with non-zero weights, but must be finite)
   {
     uint4* z = reinterpret_cast<uint4*>(smem + L.b_off);
-    const int n16 = (int)((L.w_off - L.b_off) >> 4);  // B planes, x and Y buffers
+    const int n16 = (int)((L.meta_off - L.b_off) >> 4);  // B planes, x and Y buffers
     for (int t = tid; t < n16; t += kTcThreads) z[t] = make_uint4(0u, 0u, 0u, 0u);
   }
   // A planes: rows of W_last^T (pre-scaled by 1/sqrt(H)) split into bf16 hi/mid/lo, canonical K-major layout
@@ -606,17 +714,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid
     for (int t = tid; t < a_rows * 4; t += kTcThreads) {
       const int R = t >> 2, g = t & 3;
       const int wc = P.row_wcol[R];
-      __align__(16) __nv_bfloat16 hi[8], mi[8], lo[8];
+      float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int k = g * 8 + i;
-        const float v = (wc >= 0 && k < H) ? Wl[(size_t)k * Wn + wc] * s : 0.f;
-        split_bf16x3(v, hi[i], mi[i], lo[i]);
+        v[i] = (wc >= 0 && k < H) ? Wl[(size_t)k * Wn + wc] * s : 0.f;
       }
+      uint4 hi, mi, lo;
+      tc_split8(v, hi, mi, lo);
       const size_t off = (size_t)g * a_rows * 16 + (size_t)R * 16;
-      *reinterpret_cast<uint4*>(sA + off) = *reinterpret_cast<const uint4*>(hi);
-      *reinterpret_cast<uint4*>(sA + L.a_plane + off) = *reinterpret_cast<const uint4*>(mi);
-      *reinterpret_cast<uint4*>(sA + 2 * L.a_plane + off) = *reinterpret_cast<const uint4*>(lo);
+      *reinterpret_cast<uint4*>(sA + off) = hi;
+      *reinterpret_cast<uint4*>(sA + L.a_plane + off) = mi;
+      *reinterpret_cast<uint4*>(sA + 2 * L.a_plane + off) = lo;
     }
   }
   fence_proxy_async();
@@ -625,10 +734,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
-  if (warp == kTcControlWarp) {
-    // ================================================================ control: scheduler + TMA gathers + MMA issue
-    int64_t n_cur = 0, n_end = 0;
-    int e_carry = -1;  // >= 0: the next chunk continues node n_cur at this receiver-sorted edge
+  if (warp == 0) {
+    // ================================================================ chunk builder + copies
+    int64_t n_cur, n_end;
     {
       const int64_t rank = (int64_t)blockIdx.x - P.cta_first, cnt = P.cta_count;
       auto bound = [&](int64_t i) -> int64_t {  // first node whose rowptr >= i*E/cnt
@@ -650,342 +758,194 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid
         n_end = bound(rank + 1);
       }
     }
-    bool sched_done = false;
-    int k_sched = 0;  // chunks published so far
-    // window of 32 consecutive row pointers (lane l: rowptr[w_base + l]) = 31 nodes: reloaded every ~16 nodes, so most
-    // chunks are scheduled without a global-memory round trip
+    int c_carry = -1;  // >= 0: the next chunk continues node n_cur at this padded column
+    int b_uses = 0;    // chunks that loaded the h planes so far
+    const uint32_t xrow_bytes = (uint32_t)P.x_cols * 4, ypair_bytes = (uint32_t)ystride * 4;
+    // window of 32 consecutive padded row pointers (lane l: rowptr_pad[w_base + l]) = 31 nodes
     int64_t w_base = n_cur;
-    int w_ptr = (w_base + lane <= p.N) ? p.rowptr[w_base + lane] : 0;
-    // publishes the metadata of chunk k_sched (slot k_sched % kTcMetaSlots; see the calls for why the slot is free)
-    auto schedule = [&]() {
-      const int ms = k_sched % kTcMetaSlots;
-      TcMeta& M = *reinterpret_cast<TcMeta*>(sMeta + ms * kMetaBytes);
-      int* cole = sColE + ms * 3 * NE;
+    int w_ptr = (w_base + lane <= p.N) ? p.rowptr_pad[w_base + lane] : 0;
+    MT_TC_TIMER();  // 0: chunk layout, 1: wait empty, 2: wait bfree, 3: copy issue
+    for (int k = 0;; ++k) {
+      const int b = k & 1;
+      TcMeta& M = *reinterpret_cast<TcMeta*>(sMeta + b * kMetaBytes);
       if (n_cur >= n_end) {
         if (lane == 0) {
+          mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);  // consumers released buffer b
           M.nnodes = -1;
           M.ncols = 0;
-          M.blk_next = 0;
+          mbar_arrive(&bar_go[b]);  // the gather warp sees the terminator
+          if (b_uses > 0) mbar_wait(&bar_bfree, (b_uses - 1) & 1, 20);  // the MMA warp is done with its last chunk
+          s_mma_b = -1;
+          mbar_arrive(&bar_bready);  // terminator for the MMA warp
+          mbar_arrive(&bar_full[b]);
+          mbar_arrive(&bar_full[b]);
         }
-        sched_done = true;
-      } else {
-        if (n_cur - w_base > 15) {
-          w_base = n_cur;
-          w_ptr = (w_base + lane <= p.N) ? p.rowptr[w_base + lane] : 0;
-        }
-        const int off = (int)(n_cur - w_base);
-        const int64_t cand = n_cur + lane;  // lane l looks at node n_cur + l
-        const bool in_range = cand < n_end && off + lane < 31;
-        int r_lo = __shfl_sync(0xffffffffu, w_ptr, (off + lane) & 31);
-        const int r_hi = __shfl_sync(0xffffffffu, w_ptr, (off + lane + 1) & 31);
-        if (lane == 0 && e_carry >= 0) r_lo = e_carry;
-        int deg = in_range ? r_hi - r_lo : 0;
-        bool split = false;
-        if (lane == 0 && deg > NE) {  // node larger than a chunk: take NE edges now, the rest next time
-          deg = NE;
-          split = true;
-        }
-        const int degp = (deg + 3) & ~3;
-        int cum = in_range ? degp : 0x10000;  // inclusive prefix of padded degrees
+        break;
+      }
+      if (n_cur - w_base > 15) {
+        w_base = n_cur;
+        w_ptr = (w_base + lane <= p.N) ? p.rowptr_pad[w_base + lane] : 0;
+      }
+      const int off = (int)(n_cur - w_base);
+      const int64_t cand = n_cur + lane;  // lane l looks at node n_cur + l
+      const bool in_range = cand < n_end && off + lane < 31;
+      int c_lo = __shfl_sync(0xffffffffu, w_ptr, (off + lane) & 31);
+      const int c_hi = __shfl_sync(0xffffffffu, w_ptr, (off + lane + 1) & 31);
+      if (lane == 0 && c_carry >= 0) c_lo = c_carry;
+      int degp = in_range ? c_hi - c_lo : 0;  // padded columns of the node (multiple of 4)
+      bool split = false;
+      if (lane == 0 && degp > NE) {  // node larger than a chunk: take NE columns now, the rest next time
+        degp = NE;
+        split = true;
+      }
+      int cum = in_range ? degp : 0x10000;  // inclusive prefix
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, cum, o);
-          if (lane >= o) cum += t;
-        }
-        const unsigned fm = __ballot_sync(0xffffffffu, in_range && cum <= NE);
-        int m = (fm == 0xffffffffu) ? 32 : (__ffs(~fm) - 1);  // leading run of nodes that fit
-        const bool split0 = __shfl_sync(0xffffffffu, (int)split, 0) != 0;
-        if (split0) m = 1;
-        const bool mine = lane < m;
-        const int cb = cum - degp;
-        const int ncols = __shfl_sync(0xffffffffu, cum, m - 1);
-        if (mine) {
-          M.node_id[lane] = (int)cand;
-          M.cb[lane] = (short)cb;
-          M.ngrp[lane] = (short)(degp >> 2);
-          M.first[lane] = (lane == 0 && e_carry >= 0) ? 0 : 1;
-          M.inv_den[lane] = p.num_neigh ? rsqrtf(p.num_neigh[cand]) : rsqrtf(p.avg);
-        }
-        if (lane == 0) {
-          M.nnodes = m;
-          M.ncols = ncols;
-          M.continues = (e_carry >= 0) ? 1 : 0;
-          M.blk_next = 0;
-        }
-        // per column: receiver-sorted edge (e >= 0 real edge, -2 - e: pad column = zero weights, operands of edge e),
-        // and -- resolved here, chunks ahead of their use -- the sender row and the original edge id
-        for (int j = 0; j < m; ++j) {
-          const int dj = __shfl_sync(0xffffffffu, deg, j), cj = __shfl_sync(0xffffffffu, cb, j);
-          const int rj = __shfl_sync(0xffffffffu, r_lo, j);
-          const int dpj = (dj + 3) & ~3;
-          for (int t = lane; t < dpj; t += 32) cole[cj + t] = (t < dj) ? (rj + t) : (-2 - (rj + dj - 1));
-        }
-        __syncwarp();
-        for (int c0 = 0; c0 < ncols; c0 += 64) {  // all global loads of (up to) 64 columns in flight together
-          const int c1 = c0 + lane, c2 = c0 + 32 + lane;
-          int e1 = c1 < ncols ? cole[c1] : 0, e2 = c2 < ncols ? cole[c2] : 0;
-          e1 = e1 >= 0 ? e1 : (-2 - e1);
-          e2 = e2 >= 0 ? e2 : (-2 - e2);
-          int s1 = 0, o1 = 0, s2 = 0, o2 = 0;
-          if (c1 < ncols) { s1 = p.src[e1]; o1 = p.perm[e1]; }
-          if (c2 < ncols) { s2 = p.src[e2]; o2 = p.perm[e2]; }
-          if (c1 < ncols) { cole[NE + c1] = s1; cole[2 * NE + c1] = o1; }
-          if (c2 < ncols) { cole[NE + c2] = s2; cole[2 * NE + c2] = o2; }
-        }
-        if (split0) {
-          e_carry = __shfl_sync(0xffffffffu, r_lo, 0) + NE;
-          if (e_carry >= __shfl_sync(0xffffffffu, r_hi, 0)) {  // exactly consumed
-            e_carry = -1;
-            n_cur += 1;
-          }
-        } else {
-          e_carry = -1;
-          n_cur += m;
-        }
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, cum, o);
+        if (lane >= o) cum += t;
+      }
+      const unsigned fm = __ballot_sync(0xffffffffu, in_range && cum <= NE);
+      int m = (fm == 0xffffffffu) ? 32 : (__ffs(~fm) - 1);  // leading run of nodes that fit
+      const bool split0 = __shfl_sync(0xffffffffu, (int)split, 0) != 0;
+      if (split0) m = 1;
+      const bool mine = lane < m;
+      const int cb = cum - degp;
+      const float inv_den = mine ? (p.num_neigh ? rsqrtf(p.num_neigh[cand]) : rsqrtf(p.avg)) : 0.f;
+      const int ncols = __shfl_sync(0xffffffffu, cum, m - 1);
+      const int pc0 = __shfl_sync(0xffffffffu, c_lo, 0);  // first padded column of the chunk
+      MT_TACC(0);
+      // ---- everything above only read global memory; now wait until the consumers released buffer b
+      if (lane == 0) mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);
+      __syncwarp();
+      MT_TACC(1);
+      if (mine) {
+        M.node_id[lane] = (int)cand;
+        M.cb[lane] = (short)cb;
+        M.ngrp[lane] = (short)(degp >> 2);
+        M.first[lane] = (lane == 0 && c_carry >= 0) ? 0 : 1;
+        M.inv_den[lane] = inv_den;
+      }
+      const bool continues = (c_carry >= 0);
+      if (lane == 0) {
+        M.nnodes = m;
+        M.ncols = ncols;
+        M.pc0 = pc0;
+        s_cnt[b][0] = 0; s_cnt[b][1] = 0; s_cnt[b][2] = 0; s_cnt[b][3] = 0;
+        // a chunk that continues a node split over chunks accumulates into its output row: keep the pieces
+        // ordered (deterministic sum) by letting the previous chunk drain first
+        if (continues && k > 0) mbar_wait(&bar_empty[b ^ 1], ((k - 1) >> 1) & 1, 12);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_go[ms]);
-      ++k_sched;
-    };
-    MT_TC_TIMER();  // 0: wait for a free metadata slot, 1: schedule
-    while (!sched_done) {
-      // slot k_sched % 4 was last used by chunk k_sched - 4: wait until its consumers are done.  (A barrier of its own
-      // per slot: a parity wait is only defined for the current and the preceding phase, and empty[b] may already be
-      // two chunks further.)
-      const int K = k_sched;
-      if (K >= kTcMetaSlots) {
-        if (lane == 0) mbar_wait(&bar_mfree[K % kTcMetaSlots], ((K / kTcMetaSlots) - 1) & 1, 14);
+      if (ncols == 0) {
+        if (lane == 0) {
+          mbar_arrive(&bar_go[b]);
+          mbar_arrive(&bar_full[b]);  // nothing to copy, no MMA: both arrivals from here
+          mbar_arrive(&bar_full[b]);
+        }
+      } else {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&bar_full[b], (uint32_t)ncols * xrow_bytes + (uint32_t)(ncols >> 1) * ypair_bytes);
+          mbar_arrive(&bar_go[b]);  // warp 2 issues the gathers of the sender rows (a TMA instruction costs ~250 issue
+                                    // cycles: 16 gathers + 13 bulk copies on one warp were the critical path)
+          if (b_uses > 0) mbar_wait(&bar_bfree, (b_uses - 1) & 1, 21);  // previous MMAs have consumed the h planes
+          s_mma_b = b;
+          mbar_arrive_expect_tx(&bar_bready, (uint32_t)ncols * 16u * 12u);
+        }
         __syncwarp();
+        MT_TACC(2);
+        // the chunk is ONE contiguous range of padded columns: 12 plane segments, the sh pair rows, and one TMA gather
+        // of 4 sender rows per 4 columns
+        if (lane < 12) {
+          const int pl = lane >> 2, g = lane & 3;
+          bulk_g2s(sB + (size_t)pl * L.b_plane + (size_t)g * NE * 16,
+                   reinterpret_cast<const unsigned char*>(p.hplanes) + ((size_t)(pl * 4 + g) * p.cols_max + pc0) * 16,
+                   (uint32_t)ncols * 16u, &bar_bready);
+        } else if (lane == 12) {
+          bulk_g2s(smem + L.y_off + (size_t)b * L.y_buf, p.ypairs + (size_t)(pc0 >> 1) * ystride,
+                   (uint32_t)(ncols >> 1) * ypair_bytes, &bar_full[b]);
+        }
+        ++b_uses;
+        MT_TACC(3);
       }
-      MT_TACC(0);
-      schedule();
-      MT_TACC(1);
+      // advance
+      if (split0) {
+        c_carry = pc0 + NE;
+        if (c_carry >= __shfl_sync(0xffffffffu, c_hi, 0)) {  // exactly consumed
+          c_carry = -1;
+          n_cur += 1;
+        }
+      } else {
+        c_carry = -1;
+        n_cur += m;
+      }
     }
     MT_TC_TIMER_FLUSH();
-  } else if (warp == kTcMmaWarp) {
-    // ================================================================ MMA issue (one thread; ~200 cycles per MMA: the
-    // operands travel through the uniform datapath -- a warp of its own keeps that off everybody's critical path)
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
     const uint32_t idesc = make_idesc_bf16(128, NE);
     const uint32_t a_lbo = (uint32_t)a_rows * 16, b_lbo = (uint32_t)NE * 16;
     const uint32_t a_plane32 = (uint32_t)L.a_plane, b_plane32 = (uint32_t)L.b_plane;
     const uint64_t a_desc0 = make_kmajor_desc(smem_u32(sA), a_lbo, 128);
     const uint64_t b_desc0 = make_kmajor_desc(smem_u32(sB), b_lbo, 128);
-    MT_TC_TIMER();  // 0: wait go, 1: wait bready, 2: issue
-    for (int k = 0;; ++k) {
-      const int b = k & 1, ms = k % kTcMetaSlots;
-      const TcMeta& M = *reinterpret_cast<const TcMeta*>(sMeta + ms * kMetaBytes);
-      int nn = 0, nc = 0;
+    MT_TC_TIMER();  // 0: wait bready, 1: issue
+    for (int k = 0;; ++k) {  // k counts the chunks that carry edges (and the terminator)
+      // lane 0 alone reads the hand-over word: by the time the other lanes get here the producer may already
+      // have posted the next chunk (or the terminator) -- a per-lane read would split the warp
+      int b = 0;
       if (lane == 0) {
-        mbar_wait(&bar_go[ms], (k / kTcMetaSlots) & 1, 30 + ms);
-        nn = M.nnodes;
-        nc = M.ncols;
+        mbar_wait(&bar_bready, k & 1, 30);
+        b = s_mma_b;
       }
-      nn = __shfl_sync(0xffffffffu, nn, 0);
-      nc = __shfl_sync(0xffffffffu, nc, 0);
+      b = __shfl_sync(0xffffffffu, b, 0);
       MT_TACC(0);
+      if (b < 0) break;
       if (lane == 0) {
-        if (nn < 0) {
-          mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);  // the arrival belongs to chunk k's phase of full[b]
-          mbar_arrive(&bar_full[b]);
-        } else {
-          // every chunk has one bready[b] phase (all MLP warps arrive, also for chunks without edges)
-          mbar_wait(&bar_bready[b], (k >> 1) & 1, 32 + b);
-          if (nc == 0) {
-            mbar_arrive(&bar_full[b]);  // no MMA for this chunk: plain arrival
-          } else {
-            tc_fence_after();
-            // significant products of (hi+mid+lo) x (hi+mid+lo), small ones first: planes (a, b) = (0,2) (2,0) (1,1)
-            // (0,1) (1,0) (0,0), two bits each, packed (a local array would live in local memory)
-            constexpr uint32_t kPa = 0u | (2u << 2) | (1u << 4) | (0u << 6) | (1u << 8) | (0u << 10);
-            constexpr uint32_t kPb = 2u | (0u << 2) | (1u << 4) | (1u << 6) | (0u << 8) | (0u << 10);
-            for (int t = 0; t < MT; ++t) {
-              const uint32_t d = tmem_base + (uint32_t)((b * MT + t) * NE);
-              uint32_t accum = 0;
+        tc_fence_after();
+        // significant products of (hi+mid+lo) x (hi+mid+lo), small ones first: planes (a, b) = (0,2) (2,0) (1,1) (0,1)
+        // (1,0) (0,0), two bits each, packed (a local array would live in local memory: an L2 trip per MMA)
+        constexpr uint32_t kPa = 0u | (2u << 2) | (1u << 4) | (0u << 6) | (1u << 8) | (0u << 10);
+        constexpr uint32_t kPb = 2u | (0u << 2) | (1u << 4) | (1u << 6) | (0u << 8) | (0u << 10);
+        for (int t = 0; t < MT; ++t) {
+          const uint32_t d = tmem_base + (uint32_t)((b * MT + t) * NE);
+          uint32_t accum = 0;
 #pragma unroll
-              for (int q = 0; q < 6; ++q) {
+          for (int q = 0; q < 6; ++q) {
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  // descriptors differ only in the start-address field (units of 16 bytes, no carry: < 2^14)
-                  const uint32_t a_off = ((kPa >> (2 * q)) & 3u) * a_plane32 + (uint32_t)(2 * ks) * a_lbo + (uint32_t)t * 128 * 16;
-                  const uint32_t b_off = ((kPb >> (2 * q)) & 3u) * b_plane32 + (uint32_t)(2 * ks) * b_lbo;
-                  umma_bf16(d, a_desc0 + (uint64_t)(a_off >> 4), b_desc0 + (uint64_t)(b_off >> 4), idesc, accum);
-                  accum = 1;
-                }
-              }
+            for (int ks = 0; ks < 2; ++ks) {
+              // descriptors differ only in the start-address field (units of 16 bytes, no carry: < 2^14)
+              const uint32_t a_off = ((kPa >> (2 * q)) & 3u) * a_plane32 + (uint32_t)(2 * ks) * a_lbo + (uint32_t)t * 128 * 16;
+              const uint32_t b_off = ((kPb >> (2 * q)) & 3u) * b_plane32 + (uint32_t)(2 * ks) * b_lbo;
+              umma_bf16(d, a_desc0 + (uint64_t)(a_off >> 4), b_desc0 + (uint64_t)(b_off >> 4), idesc, accum);
+              accum = 1;
             }
-            umma_commit(&bar_full[b]);
-            umma_commit(&bar_bfree);
           }
         }
+        umma_commit(&bar_full[b]);
+        umma_commit(&bar_bfree);
       }
       __syncwarp();
-      MT_TACC(2);
-      if (nn < 0) break;
+      MT_TACC(1);
     }
     MT_TC_TIMER_FLUSH();
-  } else if (warp >= kTcFirstMlpWarp) {
-    // ================================================================ radial MLP
-    const int pw = warp - kTcFirstMlpWarp;
-    const int in0 = p.sizes[0];
-    const int q4 = lane & 3, cl = lane >> 2;      // four lanes per column: lane q4 produces outputs 8 q4 .. 8 q4 + 7
-    const int yn = p.y_dim;
-    const int yq = (yn + 3) >> 2;                 // sh components per lane: [q4 * yq, min(yn, (q4 + 1) * yq))
-    float* vrow = reinterpret_cast<float*>(smem + L.v_off) + (pw * 8 + cl) * 33;  // (kTcMlpWarps rows of 8 x 33 floats)
-    int n_mma = 0;  // chunks that carried edges so far
+  } else if (warp == 2) {
+    // ================================================================ TMA gathers of the sender rows
     const CUtensorMap* map = &maps.m[part_id];
     const uint32_t xrow_bytes = (uint32_t)P.x_cols * 4;
-    MT_TC_TIMER();  // 0: wait go, 1: loads, 2: hidden layers, 3: wait empty / bfree, 4: stores + gathers, 5: claim, 6: fence + arrive + MMA
+    MT_TC_TIMER();  // 0: wait go, 1: issue
     for (int k = 0;; ++k) {
-      const int b = k & 1, ms = k % kTcMetaSlots;
-      TcMeta& M = *reinterpret_cast<TcMeta*>(sMeta + ms * kMetaBytes);
-      const int* cole = sColE + ms * 3 * NE;
-      const int* csrc = cole + NE;
-      const int* corig = cole + 2 * NE;
-      if (lane == 0) mbar_wait(&bar_go[ms], (k / kTcMetaSlots) & 1, 50 + ms);
+      const int b = k & 1;
+      const TcMeta& M = *reinterpret_cast<const TcMeta*>(sMeta + b * kMetaBytes);
+      if (lane == 0) mbar_wait(&bar_go[b], (k >> 1) & 1, 50 + b);
       __syncwarp();
       MT_TACC(0);
-      const int nn = M.nnodes, ncols = M.ncols;
-      if (nn < 0) {
-        if (lane == 0) {  // terminator: every share of full[b] (the first MT warps also the MMA commit's)
-          mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);
-          mbar_arrive(&bar_full[b]);
-        }
-        break;
+      const int nn = M.nnodes, ncols = M.ncols, pc0 = M.pc0;
+      if (nn < 0) break;
+      unsigned char* xs = smem + L.x_off + (size_t)b * L.x_buf;
+      for (int g = lane; g < (ncols >> 2); g += 32) {
+        const int4 r = *reinterpret_cast<const int4*>(p.src_pad + pc0 + 4 * g);
+        tma_gather4(xs + (size_t)(4 * g) * xrow_bytes, map, P.x_lo, r.x, r.y, r.z, r.w, &bar_full[b]);
       }
-      const int nblk = (ncols + 7) >> 3;
-      bool waited = false;
-      uint32_t tx_bytes = 0;
-      float* ys = reinterpret_cast<float*>(smem + L.y_off + (size_t)b * L.y_buf);
-      while (true) {
-        int blk = 0;
-        if (lane == 0) blk = atomicAdd(&M.blk_next, 1);
-        blk = __shfl_sync(0xffffffffu, blk, 0);
-        if (blk >= nblk) break;
-        // ---------------- loads + hidden layers of the block's 8 columns (registers and the scratch row only)
-        const int c = 8 * blk + cl;
-        const int ce = (c < ncols) ? cole[c] : -1;
-        const bool real = ce >= 0;
-        const int e = real ? ce : (ce <= -2 ? (-2 - ce) : -1);  // pad column: operands of the node's last edge
-        const bool any = e >= 0;
-        float yv[7];
-        const float* er = p.emb;
-        if (any) {
-          const int64_t orig = corig[c];
-          const float* __restrict__ yr = p.sh + orig * yn;
-#pragma unroll
-          for (int i = 0; i < 7; ++i) {
-            const int j = q4 * yq + i;
-            yv[i] = (i < yq && j < yn) ? yr[j] : 0.f;
-          }
-          er += orig * in0;
-        }
-        __syncwarp();  // the previous block of this warp has been stored
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = 8 * q4 + i;
-          vrow[idx] = (real && idx < in0) ? er[idx] : 0.f;
-        }
-        __syncwarp();
-        MT_TACC(1);
-#pragma unroll 1
-        for (int li = 0; li < nh; ++li) {
-          const int K = p.sizes[li], fo = p.sizes[li + 1];
-          const float* W = sW + (li ? wrow1 : 0) * kTcK + 8 * q4;
-          float2 a[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) a[i] = make_float2(0.f, 0.f);
-#pragma unroll 8
-          for (int kk = 0; kk < K; ++kk) {
-            const float hk = vrow[kk];
-            const float4* wr = reinterpret_cast<const float4*>(W + kk * kTcK);
-            const float4 w0 = wr[0], w1 = wr[1];
-            fma_pair(hk, w0.x, w0.y, a[0]);
-            fma_pair(hk, w0.z, w0.w, a[1]);
-            fma_pair(hk, w1.x, w1.y, a[2]);
-            fma_pair(hk, w1.z, w1.w, a[3]);
-          }
-          __syncwarp();  // all four lanes of the column have read the inputs
-          float o8[8];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            o8[2 * i] = a[i].x;
-            o8[2 * i + 1] = a[i].y;
-          }
-          if (p.act == MT_ACT_SILU) {  // the eight chains are independent: the special-function unit pipelines them
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o8[i] = o8[i] * tc_fast_sigmoid(o8[i]);
-          } else {
-#pragma unroll 1
-            for (int i = 0; i < 8; ++i) o8[i] = apply_act<float>(p.act, o8[i]);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) vrow[8 * q4 + i] = (8 * q4 + i < fo) ? o8[i] * p.act_cst : 0.f;
-          __syncwarp();
-        }
-        MT_TACC(2);
-        // ---------------- the stage must be free (consumers of chunk k - 2), and the MMAs of the previous chunk must
-        // have consumed the h planes before they are overwritten
-        if (!waited) {
-          if (lane == 0) {
-            mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);
-            if (n_mma > 0) mbar_wait(&bar_bfree, (n_mma - 1) & 1, 52);
-          }
-          __syncwarp();
-          waited = true;
-        }
-        MT_TACC(3);
-        // the block's sender rows: two TMA gathers of 4 rows (sender rows resolved by the scheduler)
-        if (lane < 2 && 8 * blk + 4 * lane < ncols) {
-          const int g = 2 * blk + lane;
-          const int4 r = *reinterpret_cast<const int4*>(csrc + 4 * g);
-          tma_gather4(smem + L.x_off + (size_t)b * L.x_buf + (size_t)(4 * g) * xrow_bytes, map, P.x_lo, r.x, r.y, r.z, r.w,
-                      &bar_full[b]);
-        }
-        tx_bytes += 4 * xrow_bytes * (uint32_t)((8 * blk < ncols) + (8 * blk + 4 < ncols));
-        if (any) {
-          // sh components -> pair-interleaved padded row: degree-l block at position sh_pad_pos(l)
-          float* yo = ys + (size_t)(c >> 1) * ystride + (c & 1);
-#pragma unroll
-          for (int i = 0; i < 7; ++i) {
-            const int j = q4 * yq + i;
-            if (i < yq && j < yn) {
-              const int l = (j >= 16) ? 4 : (j >= 9) ? 3 : (j >= 4) ? 2 : (j >= 1) ? 1 : 0;
-              yo[2 * (sh_pad_pos(l) + j - l * l)] = yv[i];
-            }
-          }
-        }
-        if (c < ncols) {
-          float h8[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) h8[i] = real ? vrow[8 * q4 + i] : 0.f;  // pad column: zero weights
-          uint4 hi, mi, lo;
-          tc_split8(h8, hi, mi, lo);
-          unsigned char* dst = sB + (size_t)q4 * NE * 16 + (size_t)c * 16;  // k-group q4 of the column
-          *reinterpret_cast<uint4*>(dst) = hi;
-          *reinterpret_cast<uint4*>(dst + L.b_plane) = mi;
-          *reinterpret_cast<uint4*>(dst + 2 * L.b_plane) = lo;
-        }
-        MT_TACC(4);
-      }
-      if (!waited && lane == 0) mbar_wait(&bar_empty[b], ((k >> 1) & 1) ^ 1, 10 + b);  // arrivals belong to chunk k's phase
-      MT_TACC(5);
-      if (pw == 0 && lane == 0) {
-        s_cnt[b][0] = 0; s_cnt[b][1] = 0; s_cnt[b][2] = 0; s_cnt[b][3] = 0;
-        // a chunk that continues a node split over chunks accumulates into its output row: keep the pieces
-        // ordered (deterministic sum) by letting the previous chunk drain first
-        if (M.continues && k > 0) mbar_wait(&bar_empty[b ^ 1], ((k - 1) >> 1) & 1, 12);
-      }
-      if (ncols > 0) fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&bar_bready[b]);
-        // this warp's sh rows of the chunk and the bytes of the gathers it issued
-        if (tx_bytes) mbar_arrive_expect_tx(&bar_full[b], tx_bytes);
-        else mbar_arrive(&bar_full[b]);
-      }
-      __syncwarp();
-      if (ncols > 0) ++n_mma;
-      MT_TACC(6);
+      MT_TACC(1);
     }
     MT_TC_TIMER_FLUSH();
   } else {
@@ -1000,7 +960,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid
       __syncwarp();
       MT_TACC(0);
       tc_fence_after();
-      const TcMeta& M = *reinterpret_cast<const TcMeta*>(sMeta + (k % kTcMetaSlots) * kMetaBytes);
+      const TcMeta& M = *reinterpret_cast<const TcMeta*>(sMeta + b * kMetaBytes);
       const int nn = M.nnodes;
       if (nn < 0) break;
       TcUnit u;
@@ -1052,10 +1012,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&bar_empty[b]);
-        mbar_arrive(&bar_mfree[k % kTcMetaSlots]);
-      }
+      if (lane == 0) mbar_arrive(&bar_empty[b]);
       MT_TACC(1);
     }
     MT_TC_TIMER_FLUSH();
