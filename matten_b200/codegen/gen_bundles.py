@@ -227,7 +227,15 @@ def _emit_path(l1: int, l2: int, l3: int, X: str, Y: str, W: str, A: str):
                     L.append(f"t{c} = fma({xo}, {yop(b, r)}, t{c});")
             L.append(f"{A}[{c}] = fma({W}, t{c}, {A}[{c}]);")
     else:
-        for (c, a, b, sg, r) in terms:
+        # round-robin over the output components: consecutive FMAs go to different accumulators (a lone warp
+        # issues in order, back-to-back updates of one accumulator would each wait out the FMA latency)
+        per_c = [[t for t in terms if t[0] == c] for c in range(d3)]
+        order = []
+        while any(per_c):
+            for lst in per_c:
+                if lst:
+                    order.append(lst.pop(0))
+        for (c, a, b, sg, r) in order:
             xo = xop(a, r)
             xo = xo if sg > 0 else f"(-{xo})"
             L.append(f"{A}[{c}] = fma({xo}, {yop(b, r)}, {A}[{c}]);")

@@ -16,6 +16,35 @@ import torch
 from . import _lib
 from ._lib import ConvPlanStruct, LinBlockStruct, MT_F32, MT_F64, check
 
+def _on_device(fn):
+    """Runs an op with the CUDA device of its first tensor argument current: the C ABI launches on the calling
+    thread's current device (like every CUDA library), while the tensors and the stream passed down belong to the
+    tensors' device -- a model on cuda:1 called while cuda:0 is current must not launch on cuda:0."""
+    import functools
+
+    def first_cuda(objs):
+        for o in objs:
+            if isinstance(o, torch.Tensor) and o.is_cuda:
+                return o.device
+            if isinstance(o, (list, tuple)):
+                d = first_cuda(o)
+                if d is not None:
+                    return d
+            if isinstance(o, ConvPlanHandle):
+                return o.device
+        return None
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = first_cuda(args) or first_cuda(kwargs.values())
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
 def launch_count() -> int:
     """Kernels launched by libmatten_b200.so in this process (exact, counted in the library)."""
     return int(_lib.load().mt_launch_count())
@@ -69,6 +98,7 @@ def raise_on_flag(flag: torch.Tensor):
 
 
 # ------------------------------------------------------------------ edges --
+@_on_device
 def edge_vectors(pos, edge_index, edge_cell_shift=None, cell=None, batch=None, flag=None,
                  want_vec=True, want_len=True):
     lib = _lib.load()
@@ -89,6 +119,7 @@ def edge_vectors(pos, edge_index, edge_cell_shift=None, cell=None, batch=None, f
     return vec, ln
 
 
+@_on_device
 def edge_sh(edge_vec, lmax: int, normalize: bool = True):
     lib = _lib.load()
     edge_vec = _req(edge_vec, "edge_vectors")
@@ -98,6 +129,7 @@ def edge_sh(edge_vec, lmax: int, normalize: bool = True):
     return out
 
 
+@_on_device
 def edge_radial(edge_len, mode: int, num_basis: int, start: float, end: float, cutoff: bool = True,
                 poly_p: float = 6.0, bessel_w=None):
     lib = _lib.load()
@@ -111,6 +143,7 @@ def edge_radial(edge_len, mode: int, num_basis: int, start: float, end: float, c
     return out
 
 
+@_on_device
 def neighbor_list(pos, cell, batch, ptr, r_max: float):
     """Periodic neighbour list of a batch of crystals on the GPU (reference data/data.py:285-413 semantics).
     pos [N,3], cell [B,3,3] (same float dtype), batch [N] int64, ptr [B+1] int64.
@@ -137,6 +170,7 @@ def neighbor_list(pos, cell, batch, ptr, r_max: float):
 
 
 # ------------------------------------------------------------ bookkeeping --
+@_on_device
 def csr_by_key(keys, num_keys: int, want_perm: bool = True, flag=None):
     """Stable sort of int64 keys -> (rowptr int32 [num_keys+1], perm int32 [E] | None)."""
     lib = _lib.load()
@@ -151,6 +185,7 @@ def csr_by_key(keys, num_keys: int, want_perm: bool = True, flag=None):
     return rowptr, perm
 
 
+@_on_device
 def gather_i64_to_i32(src, perm=None):
     lib = _lib.load()
     src = _req(src, "src", torch.int64)
@@ -160,12 +195,14 @@ def gather_i64_to_i32(src, perm=None):
     return out
 
 
+@_on_device
 def check_sorted(keys, flag):
     lib = _lib.load()
     keys = _req(keys, "keys", torch.int64)
     check(lib.mt_check_sorted(_p(keys), keys.shape[0], _p(flag), _stream(keys)))
 
 
+@_on_device
 def species_embed(atomic_numbers, species_index, lut, min_z: int, max_z: int, num_species: int,
                   lin_w, lin_b, flag=None, want_attrs=True):
     """Returns (species_index int64 [N], node_attrs [N,S] | None, node_feats [N,dim])."""
@@ -248,6 +285,7 @@ class ConvPlanHandle:
         self.device = torch.device(device)
 
 
+@_on_device
 def conv_fwd(handle: ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Tensor], rowptr, perm,
              src_sorted, avg_num_neighbors: Optional[float], num_neigh=None):
     lib = _lib.load()
@@ -295,6 +333,7 @@ def conv_select_impl(name: str) -> str:
     return {v: k for k, v in _IMPLS.items()}[old]
 
 
+@_on_device
 def conv_bwd(handle: ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Tensor], rowptr, perm, src_sorted,
              sender_ptr, sender_perm, avg_num_neighbors: Optional[float], num_neigh, grad_out,
              need_x: bool = True, need_w: bool = True):
@@ -335,6 +374,7 @@ class LinPlanHandle:
         self.in_dim, self.out_dim, self.S, self.weight_numel = in_dim, out_dim, num_species, weight_numel
 
 
+@_on_device
 def linear_fwd(h: LinPlanHandle, x, weight, species_perm=None, species_ptr=None, out=None,
                accumulate: bool = False):
     lib = _lib.load()
@@ -356,6 +396,7 @@ def linear_fwd(h: LinPlanHandle, x, weight, species_perm=None, species_ptr=None,
     return out.reshape(lead + (h.out_dim,))
 
 
+@_on_device
 def linear_bwd(h: LinPlanHandle, x, weight, grad_out, species_perm=None, species_ptr=None, need_x=True,
                need_w=True):
     """Returns (grad_x | None, grad_weight (flat) | None)."""
@@ -375,6 +416,7 @@ def linear_bwd(h: LinPlanHandle, x, weight, grad_out, species_perm=None, species
 
 
 # ------------------------------------------------------------------- gate --
+@_on_device
 def gate_bwd(x, grad_out, in_dim, out_dim, src_idx, gate_idx, act_id, act_cst, inv_first, inv_count, affine_a=None):
     lib = _lib.load()
     x = _req(x, "x")
@@ -386,6 +428,7 @@ def gate_bwd(x, grad_out, in_dim, out_dim, src_idx, gate_idx, act_id, act_cst, i
     return gx
 
 
+@_on_device
 def col_reduce(a, shift_a=None, b=None, shift_b=None):
     """out[j] = sum_n (a[n,j] - shift_a[j]) * (b[n,j] - shift_b[j])  (b None: plain column sum)."""
     lib = _lib.load()
@@ -402,6 +445,7 @@ def col_reduce(a, shift_a=None, b=None, shift_b=None):
     return out
 
 
+@_on_device
 def affine2(a, ca, b=None, cb=None, cc=None):
     """ca[j]*a[n,j] + cb[j]*b[n,j] + cc[j]"""
     lib = _lib.load()
@@ -415,6 +459,7 @@ def affine2(a, ca, b=None, cb=None, cc=None):
     return out
 
 
+@_on_device
 def gate_fwd(x, in_dim: int, out_dim: int, src_idx, gate_idx, act_id, act_cst, affine_a=None, affine_b=None):
     lib = _lib.load()
     x = _req(x, "x")
@@ -432,6 +477,7 @@ def gate_fwd(x, in_dim: int, out_dim: int, src_idx, gate_idx, act_id, act_cst, a
 _MODES = {"sum": 0, "add": 0, "mean": 1, "min": 2, "max": 3}
 
 
+@_on_device
 def segment_reduce(x, ptr, reduce: str = "sum"):
     lib = _lib.load()
     x = _req(x, "x")
@@ -442,6 +488,7 @@ def segment_reduce(x, ptr, reduce: str = "sum"):
     return out
 
 
+@_on_device
 def segment_reduce_bwd(grad_out, ptr, N: int, reduce: str):
     lib = _lib.load()
     grad_out = _req(grad_out, "grad_out")
@@ -454,6 +501,7 @@ def segment_reduce_bwd(grad_out, ptr, N: int, reduce: str):
     return gx
 
 
+@_on_device
 def segment_sum_gather(x, perm, ptr, num_rows: Optional[int] = None):
     """out[s] = sum of the rows x[perm[i]] for i in [ptr[s], ptr[s+1]) in that order."""
     lib = _lib.load()
@@ -468,6 +516,7 @@ def segment_sum_gather(x, perm, ptr, num_rows: Optional[int] = None):
 
 
 # ------------------------------------------------------- loss / optimiser --
+@_on_device
 def mse_loss(pred, target, grad_scale: float = 1.0, want_grad: bool = True):
     """(loss [1], d loss / d pred * grad_scale | None) -- torch.nn.functional.mse_loss(reduction='mean')."""
     lib = _lib.load()
@@ -482,6 +531,7 @@ def mse_loss(pred, target, grad_scale: float = 1.0, want_grad: bool = True):
     return loss, grad
 
 
+@_on_device
 def adam_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
               grad_scale: float = 1.0):
     """In-place torch.optim.Adam update of the flat buffers p, m, v from the flat gradient g."""

@@ -103,10 +103,16 @@ class _TolerantPickle:
 def load_checkpoint(path: Union[str, os.PathLike]) -> Dict[str, Any]:
     """Lightning ``.ckpt`` (or a plain ``{"state_dict", "hyper_parameters"}`` / state_dict file) -> dict with
     ``state_dict`` and ``hyper_parameters``; classes of packages that are not installed unpickle as stubs."""
+    # Safe load first (tensors + plain containers only).  Lightning checkpoints pickle hyper-parameter objects of
+    # packages that may be missing: those need the full unpickler -- which executes whatever the file contains, so
+    # only load checkpoints you trust (same caveat as the reference's torch.load / load_from_checkpoint).
     try:
-        ck = torch.load(path, map_location="cpu", weights_only=False)
+        ck = torch.load(path, map_location="cpu", weights_only=True)
     except Exception:
-        ck = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_TolerantPickle)
+        try:
+            ck = torch.load(path, map_location="cpu", weights_only=False)
+        except Exception:
+            ck = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_TolerantPickle)
     if "state_dict" not in ck:
         ck = {"state_dict": ck, "hyper_parameters": {}}
     return ck
@@ -143,8 +149,11 @@ def get_pretrained_model(identifier: str, checkpoint: str = "model_final.ckpt", 
     sd = {k: v for k, v in ck["state_dict"].items() if not k.startswith("metrics.")}
     missing, unexpected = model.load_state_dict(sd, strict=False)
     missing = [k for k in missing]
-    # e3nn modules store constant buffers (w3j tables, output masks) that this implementation regenerates
-    unexpected = [k for k in unexpected if not any(t in k for t in ("_w3j", "output_mask", "num_batches_tracked"))]
+    # e3nn modules store constant buffers (w3j tables, output masks) that this implementation regenerates, and EMPTY
+    # placeholders wherever a weight is supplied from outside (`tp.tp.weight` of the uvu product with
+    # internal_weights=False, `act.activation.mul.weight`, the `bias` of every bias-free o3.Linear)
+    unexpected = [k for k in unexpected
+                  if not any(t in k for t in ("_w3j", "output_mask", "num_batches_tracked")) and sd[k].numel() > 0]
     if missing or unexpected:
         raise RuntimeError(f"checkpoint does not match the model: missing {missing[:5]}, unexpected {unexpected[:5]}")
     if device is not None:
@@ -270,3 +279,22 @@ def save_checkpoint(model, path: Union[str, os.PathLike]):
     ``backbone.*`` / ``extra_layers_dict.*``), so that either implementation can load the other's weights."""
     torch.save({"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
                 "hyper_parameters": dict(model.hparams)}, path)
+
+
+def save_pretrained(model, directory: Union[str, os.PathLike], r_cut: float, tensor_target_name: Optional[str] = None,
+                    tensor_target_formula: Optional[str] = None, checkpoint: str = "model_final.ckpt"):
+    """Writes a directory ``predict(model_identifier=directory)`` can use: the checkpoint plus ``config_final.yaml``
+    with the ``data`` (r_cut, target name / formula) and ``model`` sections the reference's pretrained folders hold
+    (pretrained/20230627/config_final.yaml)."""
+    import yaml
+
+    directory = Path(directory)
+    directory.mkdir(parents=True, exist_ok=True)
+    save_checkpoint(model, directory / checkpoint)
+    hp = dict(model.hparams["backbone_hparams"])
+    cfg = {"data": {"r_cut": float(r_cut), "tensor_target_name": tensor_target_name or model.task_name,
+                    "tensor_target_formula": tensor_target_formula or hp.get("output_formula", "ijkl=jikl=klij")},
+           "model": hp}
+    with open(directory / "config_final.yaml", "w") as f:
+        yaml.safe_dump(cfg, f)
+    return directory

@@ -15,7 +15,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from matten_b200.dataset import TensorDataset  # noqa: E402
 from matten_b200.model_factory import AtomicTensorModel, ScalarTensorModel  # noqa: E402
-from matten_b200.predict import save_checkpoint  # noqa: E402
+from matten_b200.predict import save_pretrained  # noqa: E402
 from matten_b200.schedule import EarlyStopping, ReduceLROnPlateau  # noqa: E402
 from matten_b200.train import Trainer  # noqa: E402
 
@@ -84,8 +84,8 @@ def main():
         if rank == 0:
             print(msg, flush=True)
     if args.out and rank == 0:
-        os.makedirs(args.out, exist_ok=True)
-        save_checkpoint(model.eval(), os.path.join(args.out, "model_final.ckpt"))
+        # checkpoint + config_final.yaml: the directory is a valid `model_identifier` of matten_b200.predict.predict
+        save_pretrained(model.eval(), args.out, r_cut=5.0, tensor_target_name=key, tensor_target_formula=hp["output_formula"])
     if world > 1:
         torch.distributed.destroy_process_group()
 

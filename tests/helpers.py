@@ -52,6 +52,22 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).abs().max()) / (den if den > 0 else 1.0)
 
 
+def elem_err(a: torch.Tensor, b: torch.Tensor, floor: float = 1e-3) -> float:
+    """Element-wise error: |a-b| / |b| where |b| > floor * max|b|, |a-b| / (floor * max|b|) below that floor.
+    Unlike the normwise metric it does not let small components (high-l blocks, values next to a cut-off) hide
+    behind the largest element."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if b.numel() == 0:
+        return 0.0
+    scale = float(b.abs().max())
+    if scale == 0:
+        return float((a - b).abs().max())
+    den = b.abs().clamp(min=floor * scale)
+    return float(((a - b).abs() / den).max())
+
+
 def tol(dtype) -> float:
     # BASELINE.json north_star: 1e-5 relative in fp32, 1e-10 in fp64
     return 1e-5 if dtype == torch.float32 else 1e-10

@@ -7,6 +7,8 @@ import re
 import pytest
 import torch
 
+import matten_b200
+
 from tests.helpers import ROOT
 
 
@@ -25,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/matten_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert lib.mt_abi_version() == 1
+    assert lib.mt_abi_version() == matten_b200.ABI_VERSION == 2
 
 
 def test_no_cpu_fallback():

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import rel_err, tol
+from tests.helpers import elem_err, rel_err, tol
 
 pytestmark = pytest.mark.gpu
 DTYPES = [torch.float32, torch.float64]
@@ -87,13 +87,16 @@ def test_edge_vectors_sh_radial(dev, dtype):
         ref = E.spherical_harmonics(lmax, ob["edge_vectors"], True, "component")
         assert rel_err(sh, ref) < tol(dtype), lmax
     emb = ops.edge_radial(ln, 0, 8, 0.0, 5.0, True)
+    # The yardstick is the oracle evaluated in fp64 on the SAME lengths the kernel saw: north-star bound 1e-5 (fp32),
+    # normwise and element-wise.  (Round 1 compared with the fp32 CPU evaluation and once saw 1.5e-4; 300 repetitions
+    # of this kernel on a B200 are bitwise identical and 1.2e-6 from fp64, initcheck clean -- profiles/
+    # r2_bessel_repeat.json -- so the bound is back where the north star puts it; the fp32 CPU evaluation is only
+    # required to agree with fp64 to the same 1e-5, which keeps a libm regression on the host visible as such.)
+    ref64 = E.soft_one_hot_linspace_bessel(ln.cpu().double(), 0.0, 5.0, 8, True) * math.sqrt(8)
+    assert rel_err(emb, ref64) < tol(dtype)
+    assert elem_err(emb, ref64) < (2e-4 if dtype == torch.float32 else 1e-9)  # sin(n pi x / c) / x near its zeros
     ref = E.soft_one_hot_linspace_bessel(ob["edge_lengths"], 0.0, 5.0, 8, True) * math.sqrt(8)
-    # sin() of an O(25) argument: a few ulp of the argument.  fp32: one run in ~15 (always the first test process on a
-    # fresh box) measured 1.5e-4 here with every other run at ~1e-6 and the fp64 case exact -- the CPU oracle's
-    # vectorised fp32 sin is the suspect (unresolved); the bound below is the fp32 one for that.
-    assert rel_err(emb, ref) < (3e-4 if dtype == torch.float32 else 3 * tol(dtype))
-    ref64 = E.soft_one_hot_linspace_bessel(ob["edge_lengths"].double(), 0.0, 5.0, 8, True) * math.sqrt(8)
-    assert rel_err(emb, ref64) < (3e-4 if dtype == torch.float32 else 3 * tol(dtype))  # vs the fp64 evaluation
+    assert rel_err(emb, ref) < (2 * tol(dtype) if dtype == torch.float32 else 3 * tol(dtype))
     # cut-off edge cases: beyond r_max -> 0
     far = torch.tensor([4.999, 5.0, 5.5, 7.0], dtype=dtype)
     got = ops.edge_radial(far.to(dev), 0, 8, 0.0, 5.0, True).cpu()
@@ -429,3 +432,20 @@ def ops_neighbor(dev, sb, ptr):
     from matten_b200 import ops
 
     return ops.neighbor_list(sb["pos"].to(dev), sb["cell"].reshape(-1, 3, 3).to(dev), sb["batch"].to(dev), ptr.to(dev), 5.0)
+
+
+def test_ops_follow_the_tensor_device_not_the_current_one():
+    """A model / tensor on cuda:1 while cuda:0 is the current device: the C ABI launches on the current device, so the
+    op layer must switch to the tensors' device around every call.  Needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from matten_b200 import ops
+
+    torch.cuda.set_device(0)
+    d1 = torch.device("cuda:1")
+    vec = torch.randn(1000, 3, device=d1)
+    got = ops.edge_sh(vec, 2)
+    with torch.cuda.device(d1):
+        want = ops.edge_sh(vec, 2)
+    assert got.device == d1 and torch.equal(got, want)
+    assert torch.cuda.current_device() == 0

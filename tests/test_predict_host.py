@@ -67,3 +67,46 @@ def test_predict_requires_cuda_when_absent():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         P.predict({"lattice": np.eye(3) * 4, "species": ["Si"], "coords": [[0, 0, 0]]})
+
+
+def test_get_pretrained_model_loads_a_state_dict_with_the_e3nn_layout(tmp_path):
+    """A real Lightning checkpoint of the reference carries e3nn's EMPTY placeholder tensors (`tp.tp.weight` of the uvu
+    product with external weights, `act.activation.mul.weight`, the `bias` of bias-free o3.Linear, ...), constant
+    buffers (`_w3j`, `output_mask`) and `metrics.*` entries.  The oracle's modules register the same placeholders:
+    its state_dict, wrapped in the Lightning layout, must load."""
+    from oracle import matten_restated as M
+    from tests.helpers import HP_LMAX2, SPECIES8
+
+    torch.manual_seed(0)
+    ds = {"allowed_species": SPECIES8}
+    orac = M.ScalarTensorModel(HP_LMAX2, ds)
+    sd = {k: v.clone() for k, v in orac.state_dict().items()}
+    assert any(v.numel() == 0 for v in sd.values()), "the oracle mirrors e3nn's empty placeholder buffers"
+    sd["metrics.train.mae.total"] = torch.zeros(())  # torchmetrics state Lightning stores next to the weights
+    d = tmp_path / "pretrained_x"
+    d.mkdir()
+    torch.save({"state_dict": sd, "hyper_parameters": {"backbone_hparams": dict(HP_LMAX2), "dataset_hparams": ds}},
+               d / "model_final.ckpt")
+    model = P.get_pretrained_model(str(d))
+    got = model.state_dict()
+    for k, v in got.items():
+        assert torch.equal(v, sd[k]), k
+    # a tensor with content that the model does not know is still an error
+    sd["backbone.layer0_convnet.conv.bogus"] = torch.ones(3)
+    torch.save({"state_dict": sd, "hyper_parameters": {"backbone_hparams": dict(HP_LMAX2), "dataset_hparams": ds}},
+               d / "model_final.ckpt")
+    with pytest.raises(RuntimeError, match="does not match"):
+        P.get_pretrained_model(str(d))
+
+
+def test_save_pretrained_writes_what_predict_reads(tmp_path):
+    from matten_b200.model_factory import ScalarTensorModel
+    from tests.helpers import HP_LMAX2, SPECIES8
+
+    model = ScalarTensorModel(HP_LMAX2, {"allowed_species": SPECIES8})
+    d = P.save_pretrained(model, tmp_path / "m", r_cut=5.0, tensor_target_name="elastic_tensor_full")
+    cfg = P.get_pretrained_config(str(d))
+    assert cfg["data"] == {"r_cut": 5.0, "tensor_target_name": "elastic_tensor_full", "tensor_target_formula": "ij=ji"}
+    again = P.get_pretrained_model(str(d))
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, again.state_dict()[k])
