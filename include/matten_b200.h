@@ -102,7 +102,9 @@ int mt_edge_sh(int dtype, const void* edge_vec, int64_t E, int lmax, int normali
  *          (EdgeLengthEmbedding, reference src/matten/nn/embedding.py:185-203);
  *  mode 1: BesselBasis(r_max=end) * PolynomialCutoff(r_max=end, p)  (RadialBasisEdge-
  *          Encoding, reference src/matten/nn/_nequip.py:43-126,180-210); bessel_w [n]
- *          holds the (trainable) frequencies, NULL means n*pi. */
+ *          holds the (trainable) frequencies, NULL means n*pi;
+ *  mode 2: d(mode 1)/d bessel_w[k] per (edge, k) -- the frequency gradient is its column-wise
+ *          product sum with the incoming gradient (mt_col_reduce). */
 int mt_edge_radial(int dtype, const void* edge_len, int64_t E, int mode, int num_basis,
                    double start, double end, int cutoff, double poly_p, const void* bessel_w,
                    void* edge_emb, mt_stream stream);
@@ -379,6 +381,51 @@ int mt_adam_step(int dtype, void* p, const void* g, void* m, void* v, int64_t n,
  * mode: 0 sum, 1 mean, 2 min, 3 max.  x [N,dim] -> out [B,dim]. */
 int mt_segment_reduce(int dtype, const void* x, const int32_t* ptr, int dim, int64_t B,
                       int mode, void* out, mt_stream stream);
+
+/* Backward of mt_segment_reduce for mode 2 (min) / 3 (max): the gradient of a segment's column goes to the first
+ * row holding the extreme value, every other row of the segment gets 0 (torch_scatter's arg-based backward).
+ * x [N,dim] is the forward input; grad_x [N,dim] must cover exactly the rows ptr spans. */
+int mt_segment_extreme_bwd(int dtype, const void* x, const void* grad_out, const int32_t* ptr, int dim, int64_t B,
+                           int mode, void* grad_x, mt_stream stream);
+
+/* f4: graph-wise InstanceNorm (reference src/matten/nn/utils.py:448-588, ``NormalizationLayer(method="instance")``
+ * at :421-426).  Every graph is an instance, its nodes the samples.  Channel c (one copy of one irrep) owns the
+ * columns [chan_first[c], chan_first[c] + chan_dim[c]); chan_scalar[c] is the index among the l = 0 channels (either
+ * parity, as the reference tests ``ir.l == 0``) or -1.  l = 0 channels are centred by the graph mean; the squared
+ * norm is averaged (normalization 0, "component") or summed (1, "norm") over the 2l+1 components, then reduced over
+ * the graph's nodes by mean (reduce 0) or max (1); y = (x - mean) * (v + eps)^-1/2 * weight[c] (+ bias[scalar]).
+ * The same statistics are used in training and evaluation, as in the reference.  graph_ptr [G+1] spans the nodes of
+ * each graph (sorted batch vector).  weight [num_channels] / bias [num_scalar] may be NULL (affine=False).
+ * save_mean, save_rstd [G,num_channels] (always double: the statistics are evaluated in double for either dtype,
+ * centring subtracts nearly equal numbers) and save_arg [G,num_channels] (row chosen by the max reduce) feed
+ * the backward.  Backward: grad_x [N,dim]; grad_weight_part / grad_bias_part [G,num_channels] per-graph partial
+ * sums (either may be NULL) that the caller adds over graphs with mt_col_reduce. */
+int mt_instance_norm_fwd(int dtype, const void* x, const int32_t* graph_ptr, int64_t G, int dim, int num_channels,
+                         const int32_t* chan_first, const int32_t* chan_dim, const int32_t* chan_scalar,
+                         const void* weight, const void* bias, double eps, int reduce, int normalization, void* out,
+                         void* save_mean, void* save_rstd, int32_t* save_arg, mt_stream stream);
+int mt_instance_norm_bwd(int dtype, const void* x, const void* grad_out, const int32_t* graph_ptr, int64_t G, int dim,
+                         int num_channels, const int32_t* chan_first, const int32_t* chan_dim,
+                         const int32_t* chan_scalar, const void* weight, int reduce, int normalization,
+                         const void* save_mean, const void* save_rstd, const int32_t* save_arg, void* grad_x,
+                         void* grad_weight_part, void* grad_bias_part, mt_stream stream);
+
+/* f4: e3nn.nn.NormActivation(irreps, f, normalize=True, epsilon=1e-8, bias=False) as the reference builds it
+ * (src/matten/nn/utils.py:142-150, ``activation_type="norm"``): per channel n = sqrt(max(sum_m x_m^2, epsilon^2)),
+ * y_m = x_m * f(n) / n with f the raw activation act_id (MT_ACT_*, no second-moment constant).  The backward
+ * treats a clamped norm as a constant, as autograd does for the masked assignment. */
+int mt_norm_act_fwd(int dtype, const void* x, int dim, int num_channels, const int32_t* chan_first,
+                    const int32_t* chan_dim, int act_id, double epsilon, void* out, int64_t N, mt_stream stream);
+int mt_norm_act_bwd(int dtype, const void* x, const void* grad_out, int dim, int num_channels,
+                    const int32_t* chan_first, const int32_t* chan_dim, int act_id, double epsilon, void* grad_x,
+                    int64_t N, mt_stream stream);
+
+/* f4: target normalisers (reference src/matten/data/transform.py:116-133 MeanNormNormalize, :265-279
+ * ScalarNormalize).  inverse 0: out = (data - mean) / (norm * scale); inverse 1: out = data * (norm * scale) + mean,
+ * each operation rounded separately as the reference's elementwise expressions are.  data/out [N,dim], mean/norm
+ * [dim].  The statistics themselves (compute_statistics, :139-216) are column reductions: mt_col_reduce. */
+int mt_normalize(int dtype, const void* data, const void* mean, const void* norm, double scale, int inverse,
+                 void* out, int64_t N, int dim, mt_stream stream);
 
 #ifdef __cplusplus
 }

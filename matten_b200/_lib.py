@@ -97,6 +97,12 @@ SIGNATURES = {
     "mt_linear_fwd": (_I, [_I, C.POINTER(LinBlockStruct), _I, _I, _I, _I, _V, _V, _V, _V, _I, _V, _L, _V]),
     "mt_gate_fwd": (_I, [_I, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _L, _V]),
     "mt_segment_reduce": (_I, [_I, _V, _V, _I, _L, _I, _V, _V]),
+    "mt_segment_extreme_bwd": (_I, [_I, _V, _V, _V, _I, _L, _I, _V, _V]),
+    "mt_instance_norm_fwd": (_I, [_I, _V, _V, _L, _I, _I, _V, _V, _V, _V, _V, _D, _I, _I, _V, _V, _V, _V, _V]),
+    "mt_instance_norm_bwd": (_I, [_I, _V, _V, _V, _L, _I, _I, _V, _V, _V, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V]),
+    "mt_norm_act_fwd": (_I, [_I, _V, _I, _I, _V, _V, _I, _D, _V, _L, _V]),
+    "mt_norm_act_bwd": (_I, [_I, _V, _V, _I, _I, _V, _V, _I, _D, _V, _L, _V]),
+    "mt_normalize": (_I, [_I, _V, _V, _V, _D, _I, _V, _L, _I, _V]),
 }
 
 _lock = threading.Lock()

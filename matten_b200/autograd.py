@@ -118,11 +118,78 @@ class SegmentReduceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ptr, reduce):
         ctx.ptr, ctx.reduce, ctx.N = ptr, reduce, x.shape[0]
+        if reduce in ("min", "max"):
+            ctx.save_for_backward(x)
         return ops.segment_reduce(x.detach(), ptr, reduce)
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.reduce in ("min", "max"):
+            (x,) = ctx.saved_tensors
+            return ops.segment_extreme_bwd(x.detach(), g.contiguous(), ctx.ptr, ctx.reduce), None, None
         return ops.segment_reduce_bwd(g.contiguous(), ctx.ptr, ctx.N, ctx.reduce), None, None
+
+
+class BesselRadialFn(torch.autograd.Function):
+    """BesselBasis x PolynomialCutoff with trainable frequencies (reference src/matten/nn/_nequip.py:80-126):
+    d out[e,k] / d w_k = (2 / r_max^2) cos(w_k r / r_max) env(r); summed over edges in fixed order."""
+
+    @staticmethod
+    def forward(ctx, bessel_w, length, num_basis, start, end, cutoff, poly_p):
+        ctx.args = (num_basis, start, end, cutoff, poly_p)
+        ctx.save_for_backward(bessel_w, length)
+        return ops.edge_radial(length, 1, num_basis, start, end, cutoff, poly_p, bessel_w.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        w, length = ctx.saved_tensors
+        num_basis, start, end, cutoff, poly_p = ctx.args
+        dw = ops.edge_radial(length, 2, num_basis, start, end, cutoff, poly_p, w.detach())
+        return ops.col_reduce(g.contiguous(), None, dw, None), None, None, None, None, None, None
+
+
+class InstanceNormFn(torch.autograd.Function):
+    """Graph InstanceNorm (reference src/matten/nn/utils.py:448-588); the per-graph partial parameter gradients
+    are summed over graphs by the fixed-order column reduction."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, graph_ptr, mod):
+        w = None if weight is None else weight.detach()
+        b = None if bias is None else bias.detach()
+        y, saved = ops.instance_norm_fwd(x.detach(), graph_ptr, mod.tables(), w, b, mod.eps, mod.reduce,
+                                         mod.normalization)
+        ctx.mod, ctx.graph_ptr, ctx.has_w = mod, graph_ptr, w is not None
+        ctx.save_for_backward(x, w if w is not None else x.new_empty(0), *saved)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, mean, rstd, arg = ctx.saved_tensors
+        mod = ctx.mod
+        need_p = ctx.has_w and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        gx, gwp, gbp = ops.instance_norm_bwd(x.detach(), g.contiguous(), ctx.graph_ptr, mod.tables(),
+                                             w if ctx.has_w else None, (mean, rstd, arg), mod.reduce,
+                                             mod.normalization, need_p)
+        gw = gb = None
+        if need_p:
+            gw = ops.col_reduce(gwp)
+            gb = ops.col_reduce(gbp).index_select(0, mod.scalar_channels)
+        return gx, gw, gb, None, None
+
+
+class NormActFn(torch.autograd.Function):
+    """e3nn NormActivation (reference src/matten/nn/utils.py:142-150)."""
+
+    @staticmethod
+    def forward(ctx, x, tables, act_id, epsilon):
+        ctx.tables, ctx.act_id, ctx.epsilon = tables, act_id, epsilon
+        ctx.save_for_backward(x)
+        return ops.norm_act(x.detach(), tables, act_id, epsilon)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.norm_act_bwd(x.detach(), g.contiguous(), ctx.tables, ctx.act_id, ctx.epsilon), None, None, None
 
 
 class _SpeciesEmbedFn(torch.autograd.Function):

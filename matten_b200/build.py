@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
 ] + (["-DMT_TC_TIMING"] if os.environ.get("MT_TC_TIMING") else [])  # phase timing of the tcgen05 conv (tools/tc_debug.py)
 
-PLAIN_SOURCES = ["api.cu", "graph_ops.cu", "node_ops.cu", "train_ops.cu", "conv.cu", "conv_fwd_tc.cu", "conv_bwd.cu"]
+PLAIN_SOURCES = ["api.cu", "graph_ops.cu", "node_ops.cu", "train_ops.cu", "norm_ops.cu", "conv.cu", "conv_fwd_tc.cu", "conv_bwd.cu"]
 CONV_INST = [(t, hp) for t in ("float", "double") for hp in (8, 16, 32, 64)]
 
 

@@ -132,7 +132,8 @@ __device__ __forceinline__ T apply_act(int id, T v) {
     case MT_ACT_SILU: return v * act_sigmoid(v);
     case MT_ACT_TANH: return act_tanh(v);
     case MT_ACT_SIGMOID: return act_sigmoid(v);
-    case MT_ACT_SSP: return act_softplus(v) - T(0.6931471805599453);
+    // softplus(v) - log 2 = log1p(expm1(v) / 2): no cancellation next to v = 0 (NormActivation feeds norms there)
+    case MT_ACT_SSP: return v > T(20) ? v - T(0.6931471805599453) : log1p(T(0.5) * expm1(v));
     case MT_ACT_ABS: return fabs(v);
     default: return v;
   }

@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256) edge_radial_kernel(const T* __restrict__ 
     v *= sqrt(T(nb));
   } else {
     T w = bessel_w ? bessel_w[k] : T(k + 1) * pi;
-    T basis = (T(2) / end) * (sin(w * r / end) / r);
+    // mode 2: derivative of the mode-1 value with respect to the frequency w_k (trainable BesselBasis)
+    T basis = mode == 2 ? (T(2) / end) * (cos(w * r / end) / end) : (T(2) / end) * (sin(w * r / end) / r);
     T u = r / end;
     T p = poly_p;
     T env = T(1) - ((p + T(1)) * (p + T(2)) / T(2)) * pow(u, p) + p * (p + T(2)) * pow(u, p + T(1)) -
@@ -509,7 +510,7 @@ int mt_edge_radial(int dtype, const void* edge_len, int64_t E, int mode, int num
                    double end, int cutoff, double poly_p, const void* bessel_w, void* edge_emb,
                    mt_stream stream) {
   MT_ENTRY_GUARD();
-  MT_REQUIRE(mode == 0 || mode == 1, "radial mode %d", mode);
+  MT_REQUIRE(mode >= 0 && mode <= 2, "radial mode %d", mode);
   MT_REQUIRE(num_basis > 0 && end > start, "bad radial basis parameters");
   if (E == 0) return MT_OK;
   MT_REQUIRE(edge_len && edge_emb, "null pointer");

@@ -43,8 +43,11 @@ def edge_sh(vec, lmax: int, normalize: bool = True):
 
 def edge_radial(length, mode, num_basis, start, end, cutoff=True, poly_p=6.0, bessel_w=None):
     if _needs_grad(bessel_w):
-        raise NotImplementedError("gradients w.r.t. trainable Bessel frequencies (RadialBasisEdgeEncoding) are not "
-                                  "implemented; no matten model factory wires that module")
+        if mode != 1:
+            raise ValueError("trainable frequencies belong to the BesselBasis encoding (mode 1)")
+        from . import autograd as A
+
+        return A.BesselRadialFn.apply(bessel_w, length.detach(), num_basis, start, end, cutoff, poly_p)
     bw = bessel_w.detach() if bessel_w is not None else None
     return ops.edge_radial(length.detach(), mode, num_basis, start, end, cutoff, poly_p, bw)
 

@@ -9,6 +9,7 @@ import torch
 
 from ..data.irreps import DataKey, ModuleIrreps
 from ..graph import get_graph
+from ._nequip import with_batch
 from ..o3 import Irreps
 from .utils import ActivationLayer, NormalizationLayer, SpeciesLinear, UVUTensorProduct
 
@@ -83,6 +84,11 @@ class PointConvWithActivation(ModuleIrreps, torch.nn.Module):
             x = self.act(x, a, b)
         else:
             x = self.act(x)
-            x = self.norm(x, data.get(DataKey.BATCH))
+            if self.norm.method == "instance":
+                with_batch(data)
+                g = get_graph(data)
+                x = self.norm(x, graph_ptr=g.graph_ptr(data[DataKey.BATCH], data.get("num_graphs")))
+            else:
+                x = self.norm(x, data.get(DataKey.BATCH))
         data[DataKey.NODE_FEATURES] = x
         return data

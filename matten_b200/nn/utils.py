@@ -183,8 +183,58 @@ class _GateModule(_Buffers):
         return F.gate(x, self.tables(x.dtype), affine_a, affine_b)
 
 
+def channel_tables(irreps: Irreps, scalar_test):
+    """Per-channel (first column, 2l+1, index among the channels ``scalar_test`` accepts or -1) int32 tables."""
+    first, cdim, scal = [], [], []
+    col = ns = 0
+    for mul, ir in irreps:
+        for _ in range(mul):
+            first.append(col)
+            cdim.append(ir.dim)
+            if scalar_test(ir):
+                scal.append(ns)
+                ns += 1
+            else:
+                scal.append(-1)
+            col += ir.dim
+    t = lambda v: torch.tensor(v, dtype=torch.int32)  # noqa: E731
+    return t(first), t(cdim), t(scal), ns
+
+
+class _NormActModule(_Buffers):
+    """e3nn ``NormActivation(irreps, f, normalize=True, epsilon=1e-8, bias=False)`` on the scalars + gated irreps
+    the tensor product can reach (reference src/matten/nn/utils.py:96-118,142-150): every channel is scaled by
+    f(|x|) / |x| with f the raw even-scalar activation."""
+
+    epsilon = 1e-8
+
+    def __init__(self, tp_irreps_in1, tp_irreps_in2, tp_irreps_out, act_name: str):
+        super().__init__()
+        out = Irreps(tp_irreps_out).sort().irreps.simplify()
+        ok = lambda ir: tp_path_exists(tp_irreps_in1, tp_irreps_in2, ir)  # noqa: E731
+        scalars = Irreps([(m, ir) for m, ir in out if ir.l == 0 and ok(ir)])
+        gated = Irreps([(m, ir) for m, ir in out if ir.l > 0 and ok(ir)])
+        self.irreps_in = self.irreps_out = (scalars + gated).simplify()
+        self.act_id = o3.ACT_FUNCS[act_name][1]
+        first, cdim, _, _ = channel_tables(self.irreps_in, lambda ir: False)
+        self._reg("chan_first", first)
+        self._reg("chan_dim", cdim)
+
+    def forward(self, x, affine_a=None, affine_b=None):
+        tables = (self.chan_first, self.chan_dim)
+        if torch.is_grad_enabled() and x.requires_grad:
+            from .. import autograd as A
+
+            y = A.NormActFn.apply(x, tables, self.act_id, self.epsilon)
+        else:
+            y = ops.norm_act(x.detach(), tables, self.act_id, self.epsilon)
+        if affine_a is not None:
+            y = A_affine(y, affine_a, affine_b)
+        return y
+
+
 class ActivationLayer(torch.nn.Module):
-    """reference src/matten/nn/utils.py:29-167 (``gate``; ``norm`` is a SURVEY section 8f row)."""
+    """reference src/matten/nn/utils.py:29-167 (``gate`` and ``norm``)."""
 
     def __init__(self, tp_irreps_in1: Irreps, tp_irreps_in2: Irreps, tp_irreps_out: Irreps, *,
                  activation_type: str = "gate", activation_scalars: Dict[str, str] = None,
@@ -202,8 +252,7 @@ class ActivationLayer(torch.nn.Module):
         if activation_type == "gate":
             self.activation = _GateModule(GatePlan(tp_irreps_in1, tp_irreps_in2, tp_irreps_out, a_s, a_g))
         elif activation_type == "norm":
-            raise NotImplementedError("nonlinearity_type 'norm' (e3nn NormActivation) is not used by any "
-                                      "shipped matten config and is not implemented yet")
+            self.activation = _NormActModule(tp_irreps_in1, tp_irreps_in2, tp_irreps_out, a_s[1])
         else:
             raise ValueError(f"Support `activation_type` includes ('gate', 'norm'), got {activation_type}")
 
@@ -302,6 +351,65 @@ def A_affine(x, a, b):
 _IDENT = {}
 
 
+class InstanceNorm(_Buffers):
+    """Graph-wise instance normalisation (reference src/matten/nn/utils.py:448-588): every graph is an instance and
+    its nodes are the samples.  l = 0 channels of either parity are centred and biased (the reference tests
+    ``ir.l == 0``); the same graph statistics are used in training and evaluation (reference note at :440-441).
+
+    ``forward(input, batch)`` takes the sorted node -> graph vector like the reference; ``graph_ptr`` (the CSR form
+    the kernels consume) can be passed instead when the caller already holds it."""
+
+    def __init__(self, irreps, eps=1e-5, affine=True, reduce="mean", normalization="component"):
+        super().__init__()
+        self.irreps = Irreps(irreps)
+        self.eps, self.affine = eps, affine
+        assert isinstance(reduce, str), "reduce should be passed as a string value"
+        assert reduce in ["mean", "max"], "reduce needs to be 'mean' or 'max'"
+        assert normalization in ["norm", "component"], "normalization needs to be 'norm' or 'component'"
+        self.reduce, self.normalization = reduce, normalization
+        first, cdim, scal, ns = channel_tables(self.irreps, lambda ir: ir.l == 0)
+        self.num_features, self.num_scalar = first.shape[0], ns
+        self._reg("chan_first", first)
+        self._reg("chan_dim", cdim)
+        self._reg("chan_scalar", scal)
+        self._reg("scalar_channels", torch.nonzero(scal >= 0).reshape(-1))
+        if affine:
+            self.weight = torch.nn.Parameter(torch.ones(self.num_features))
+            self.bias = torch.nn.Parameter(torch.zeros(self.num_scalar))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__} ({self.irreps}, eps={self.eps})"
+
+    def tables(self):
+        return self.chan_first, self.chan_dim, self.chan_scalar
+
+    def forward(self, input: Tensor, batch: Tensor = None, graph_ptr: Tensor = None) -> Tensor:
+        if input.shape[-1] != self.irreps.dim:
+            raise AssertionError(f"`ix` should have reached input.size(-1) ({input.shape[-1]}), "
+                                 f"but it ended at {self.irreps.dim}")
+        if graph_ptr is None:
+            if batch is None:
+                raise ValueError("InstanceNorm needs the node -> graph vector `batch`")
+            flag = ops.new_flag(input.device)
+            ops.check_sorted(batch, flag)
+            num_graphs = int(batch[-1].item()) + 1 if batch.numel() else 0
+            graph_ptr, _ = ops.csr_by_key(batch, num_graphs, False, flag)
+            ops.raise_on_flag(flag)
+        w = self.weight if self.affine else None
+        b = self.bias if self.affine else None
+        grad = torch.is_grad_enabled() and (input.requires_grad or (self.affine and self.weight.requires_grad))
+        if grad:
+            from .. import autograd as A
+
+            return A.InstanceNormFn.apply(input, w, b, graph_ptr, self)
+        return ops.instance_norm_fwd(input.detach(), graph_ptr, self.tables(), None if w is None else w.detach(),
+                                     None if b is None else b.detach(), self.eps, self.reduce,
+                                     self.normalization)[0]
+
+
 class NormalizationLayer(torch.nn.Module):
     """reference src/matten/nn/utils.py:397-437"""
 
@@ -310,12 +418,16 @@ class NormalizationLayer(torch.nn.Module):
         self.method = method
         supported = ("batch", "instance", "none", None)
         assert method in supported, f"Unsupported normalization {method}"
-        if method == "instance":
-            raise NotImplementedError("graph InstanceNorm is not used by any shipped matten config and is not "
-                                      "implemented yet (SURVEY section 8f)")
-        self.n = BatchNorm(irreps) if method == "batch" else None
+        if method == "batch":
+            self.n = BatchNorm(irreps)
+        elif method == "instance":
+            self.n = InstanceNorm(irreps)
+        else:
+            self.n = None
 
-    def forward(self, x: Tensor, batch: Tensor = None) -> Tensor:
+    def forward(self, x: Tensor, batch: Tensor = None, graph_ptr: Tensor = None) -> Tensor:
         if self.method == "batch":
             x = self.n(x)
+        elif self.method == "instance":
+            x = self.n(x, batch, graph_ptr)
         return x

@@ -494,11 +494,118 @@ def segment_reduce_bwd(grad_out, ptr, N: int, reduce: str):
     grad_out = _req(grad_out, "grad_out")
     B, dim = grad_out.shape
     if _MODES[reduce] > 1:
-        raise NotImplementedError("backward of min/max pooling is not implemented")
+        raise ValueError("min/max pooling backward needs the forward input: use segment_extreme_bwd")
     gx = torch.empty((N, dim), dtype=grad_out.dtype, device=grad_out.device)
     check(lib.mt_segment_reduce_bwd(_dt(grad_out), _p(grad_out), _p(ptr), dim, B, N, _MODES[reduce], _p(gx),
                                     _stream(grad_out)))
     return gx
+
+
+@_on_device
+def segment_extreme_bwd(x, grad_out, ptr, reduce: str):
+    """Backward of min/max pooling: the gradient goes to the first row holding the extreme value."""
+    lib = _lib.load()
+    x = _req(x, "x")
+    grad_out = _req(grad_out, "grad_out", x.dtype)
+    B, dim = grad_out.shape
+    if _MODES[reduce] < 2:
+        raise ValueError("segment_extreme_bwd handles min and max")
+    gx = torch.zeros_like(x)  # rows outside ptr's span (none for a batch vector) keep 0
+    check(lib.mt_segment_extreme_bwd(_dt(x), _p(x), _p(grad_out), _p(ptr), dim, B, _MODES[reduce], _p(gx),
+                                     _stream(x)))
+    return gx
+
+
+# -------------------------------------------------------- normalisation (f4) --
+_IN_REDUCE = {"mean": 0, "max": 1}
+_IN_NORMALIZATION = {"component": 0, "norm": 1}
+
+
+@_on_device
+def instance_norm_fwd(x, graph_ptr, tables, weight, bias, eps: float, reduce: str, normalization: str):
+    """Graph InstanceNorm forward; ``tables`` = (chan_first, chan_dim, chan_scalar) int32 [num_channels].
+    Returns (out, (mean, rstd, arg)) with the saved per-(graph, channel) statistics."""
+    lib = _lib.load()
+    x = _req(x, "x")
+    first, cdim, scal = tables
+    N, dim = x.shape
+    G, nf = graph_ptr.shape[0] - 1, first.shape[0]
+    out = torch.empty_like(x)
+    mean = torch.empty((G, nf), dtype=torch.float64, device=x.device)
+    rstd = torch.empty_like(mean)
+    arg = torch.empty((G, nf), dtype=torch.int32, device=x.device)
+    weight = None if weight is None else _req(weight, "weight", x.dtype)
+    bias = None if bias is None else _req(bias, "bias", x.dtype)
+    check(lib.mt_instance_norm_fwd(_dt(x), _p(x), _p(graph_ptr), G, dim, nf, _p(first), _p(cdim), _p(scal),
+                                   _p(weight), _p(bias), float(eps), _IN_REDUCE[reduce],
+                                   _IN_NORMALIZATION[normalization], _p(out), _p(mean), _p(rstd), _p(arg),
+                                   _stream(x)))
+    return out, (mean, rstd, arg)
+
+
+@_on_device
+def instance_norm_bwd(x, grad_out, graph_ptr, tables, weight, saved, reduce: str, normalization: str,
+                      need_params: bool = True):
+    """Returns (grad_x, grad_weight_part [G,nf] | None, grad_bias_part [G,nf] | None)."""
+    lib = _lib.load()
+    x = _req(x, "x")
+    grad_out = _req(grad_out, "grad_out", x.dtype)
+    first, cdim, scal = tables
+    mean, rstd, arg = saved
+    N, dim = x.shape
+    G, nf = graph_ptr.shape[0] - 1, first.shape[0]
+    gx = torch.empty_like(x)
+    gw = torch.empty((G, nf), dtype=x.dtype, device=x.device) if need_params else None
+    gb = torch.empty((G, nf), dtype=x.dtype, device=x.device) if need_params else None
+    weight = None if weight is None else _req(weight, "weight", x.dtype)
+    check(lib.mt_instance_norm_bwd(_dt(x), _p(x), _p(grad_out), _p(graph_ptr), G, dim, nf, _p(first), _p(cdim),
+                                   _p(scal), _p(weight), _IN_REDUCE[reduce], _IN_NORMALIZATION[normalization],
+                                   _p(mean), _p(rstd), _p(arg), _p(gx), _p(gw), _p(gb), _stream(x)))
+    return gx, gw, gb
+
+
+@_on_device
+def norm_act(x, tables, act_id: int, epsilon: float = 1e-8):
+    lib = _lib.load()
+    x = _req(x, "x")
+    first, cdim = tables
+    dim = x.shape[-1]
+    N = x.numel() // dim
+    out = torch.empty_like(x)
+    check(lib.mt_norm_act_fwd(_dt(x), _p(x), dim, first.shape[0], _p(first), _p(cdim), int(act_id), float(epsilon),
+                              _p(out), N, _stream(x)))
+    return out
+
+
+@_on_device
+def norm_act_bwd(x, grad_out, tables, act_id: int, epsilon: float = 1e-8):
+    lib = _lib.load()
+    x = _req(x, "x")
+    grad_out = _req(grad_out, "grad_out", x.dtype)
+    first, cdim = tables
+    dim = x.shape[-1]
+    N = x.numel() // dim
+    gx = torch.empty_like(x)
+    check(lib.mt_norm_act_bwd(_dt(x), _p(x), _p(grad_out), dim, first.shape[0], _p(first), _p(cdim), int(act_id),
+                              float(epsilon), _p(gx), N, _stream(x)))
+    return gx
+
+
+@_on_device
+def normalize(data, mean, norm, scale: float = 1.0, inverse: bool = False):
+    """(data - mean) / (norm * scale), or its inverse data * (norm * scale) + mean."""
+    lib = _lib.load()
+    data = _req(data, "data")
+    mean = _req(mean, "mean", data.dtype)
+    norm = _req(norm, "norm", data.dtype)
+    dim = data.shape[-1]
+    if mean.numel() != dim or norm.numel() != dim:
+        raise ValueError(f"mean/norm must have {dim} entries, got {mean.numel()} and {norm.numel()}")
+    N = data.numel() // dim
+    out = torch.empty_like(data)
+    check(lib.mt_normalize(_dt(data), _p(data), _p(mean), _p(norm), float(scale), int(bool(inverse)), _p(out), N, dim,
+                           _stream(data)))
+    return out
 
 
 @_on_device

@@ -607,6 +607,49 @@ class Gate(torch.nn.Module):
         return scalars
 
 
+# ----------------------------------------------------------- norm activation --
+class NormActivation(torch.nn.Module):
+    """e3nn.nn.NormActivation (e3nn 0.5.x ``nn/_normact.py``): o3.Norm(irreps, squared=True) is the plain sum of
+    squares per channel, clamped from below at epsilon^2 and square-rooted; the scalar nonlinearity acts on the norm
+    (plus an optional per-channel bias), is divided by the norm when ``normalize`` and multiplies the channel through
+    ElementwiseTensorProduct("Nx0e", irreps) -- a plain scalar * vector product under component normalisation.
+    The reference builds it with normalize=True, epsilon=1e-8, bias=False (src/matten/nn/utils.py:142-150)."""
+
+    def __init__(self, irreps_in, scalar_nonlinearity, normalize=True, epsilon=None, bias=False):
+        super().__init__()
+        self.irreps_in = self.irreps_out = parse_irreps(irreps_in)
+        if epsilon is None and normalize:
+            epsilon = 1e-8
+        elif epsilon is not None and not normalize:
+            raise ValueError("epsilon and normalize = False don't make sense together")
+        self._eps_squared = epsilon * epsilon if epsilon is not None else 0.0
+        self.scalar_nonlinearity, self.normalize, self.bias = scalar_nonlinearity, normalize, bias
+        n = sum(m for m, _, _ in self.irreps_in)
+        if bias:
+            self.biases = torch.nn.Parameter(torch.zeros(n))
+
+    def forward(self, features):
+        norms = []
+        for (m, l, p), sl in zip(self.irreps_in, irreps_slices(self.irreps_in)):
+            f = features[..., sl].reshape(features.shape[:-1] + (m, 2 * l + 1))
+            norms.append(f.pow(2).sum(-1))
+        norms = torch.cat(norms, -1)
+        if self._eps_squared > 0:
+            norms = torch.where(norms < self._eps_squared, torch.full_like(norms, self._eps_squared), norms).sqrt()
+        else:
+            norms = norms.sqrt()
+        arg = norms + self.biases if self.bias else norms
+        scalings = self.scalar_nonlinearity(arg)
+        if self.normalize:
+            scalings = scalings / norms
+        out, i = [], 0
+        for (m, l, p), sl in zip(self.irreps_in, irreps_slices(self.irreps_in)):
+            f = features[..., sl].reshape(features.shape[:-1] + (m, 2 * l + 1))
+            out.append((f * scalings[..., i:i + m, None]).reshape(features.shape[:-1] + (m * (2 * l + 1),)))
+            i += m
+        return torch.cat(out, -1)
+
+
 # ---------------------------------------------------------------- batchnorm --
 class BatchNorm(torch.nn.Module):
     """e3nn.nn.BatchNorm(irreps) defaults: eps 1e-5, momentum 0.1, affine,

@@ -286,7 +286,7 @@ class PointConv(torch.nn.Module):
 
 
 class ActivationLayer(torch.nn.Module):
-    """reference src/matten/nn/utils.py:29-167 (gate only)"""
+    """reference src/matten/nn/utils.py:29-167"""
 
     def __init__(self, tp_irreps_in1, tp_irreps_in2, tp_irreps_out, *, activation_type="gate",
                  activation_scalars=None, activation_gates=None):
@@ -305,7 +305,13 @@ class ActivationLayer(torch.nn.Module):
         ok = lambda l, p: tp_path_exists(tp_irreps_in1, tp_irreps_in2, (l, p))  # noqa: E731
         scalars = [(m, l, p) for m, l, p in out if l == 0 and ok(l, p)]
         gated = [(m, l, p) for m, l, p in out if l > 0 and ok(l, p)]
-        assert activation_type == "gate", "oracle restates the gate nonlinearity only"
+        if activation_type == "norm":
+            # norm is an even scalar, so activation_scalars[1]   (utils.py:142-150)
+            self.activation = E.NormActivation(E.irreps_simplify(scalars + gated), a_s[1], normalize=True,
+                                               epsilon=1e-8, bias=False)
+            return
+        if activation_type != "gate":
+            raise ValueError(f"Support `activation_type` includes ('gate', 'norm'), got {activation_type}")
         if E.irreps_dim(gated) > 0:
             if ok(0, 1):
                 gp = 1
@@ -331,17 +337,131 @@ class ActivationLayer(torch.nn.Module):
         return self.activation.irreps_out
 
 
+def _graph_pool(x, batch, reduce):
+    """torch_geometric global_mean_pool / global_max_pool: scatter over the node -> graph vector."""
+    G = int(batch.max()) + 1 if batch.numel() else 0
+    return E.scatter(x, batch, dim_size=G, reduce=reduce)
+
+
+class InstanceNorm(torch.nn.Module):
+    """reference src/matten/nn/utils.py:448-588: each graph is an instance, its nodes the samples; l == 0 channels
+    (either parity) are centred by the graph mean and get a bias; the channel's squared norm (component mean or
+    sum) is pooled over the graph's nodes by mean or max; the same statistics serve training and evaluation."""
+
+    def __init__(self, irreps, eps=1e-5, affine=True, reduce="mean", normalization="component"):
+        super().__init__()
+        self.irreps = E.parse_irreps(irreps)
+        self.eps, self.affine = eps, affine
+        ns = sum(m for m, l, p in self.irreps if l == 0)
+        nf = sum(m for m, _, _ in self.irreps)
+        if affine:
+            self.weight = torch.nn.Parameter(torch.ones(nf))
+            self.bias = torch.nn.Parameter(torch.zeros(ns))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+        assert reduce in ["mean", "max"] and normalization in ["norm", "component"]
+        self.reduce, self.normalization = reduce, normalization
+
+    def forward(self, input, batch):
+        fields = []
+        ix = iw = ib = 0
+        for m, l, p in self.irreps:
+            d = 2 * l + 1
+            field = input[:, ix:ix + m * d].reshape(-1, m, d)
+            ix += m * d
+            if l == 0:
+                mean = _graph_pool(field, batch, "mean").reshape(-1, m, 1)
+                field = field - mean[batch]
+            fn = field.pow(2).sum(-1) if self.normalization == "norm" else field.pow(2).mean(-1)
+            fn = _graph_pool(fn, batch, self.reduce)
+            fn = (fn + self.eps).pow(-0.5)
+            if self.affine:
+                fn = fn * self.weight[None, iw:iw + m]
+                iw += m
+            field = field * fn[batch].reshape(-1, m, 1)
+            if self.affine and d == 1:
+                field = field + self.bias[ib:ib + m].reshape(m, 1)
+                ib += m
+            fields.append(field.reshape(-1, m * d))
+        assert ix == input.shape[-1]
+        return torch.cat(fields, -1)
+
+
 class NormalizationLayer(torch.nn.Module):
-    """reference src/matten/nn/utils.py:397-437 (batch / none)"""
+    """reference src/matten/nn/utils.py:397-437"""
 
     def __init__(self, irreps, method=None):
         super().__init__()
-        assert method in ("batch", "none", None), "oracle restates batch normalisation only"
+        assert method in ("batch", "instance", "none", None), f"Unsupported normalization {method}"
         self.method = method
-        self.n = E.BatchNorm(irreps) if method == "batch" else None
+        self.n = E.BatchNorm(irreps) if method == "batch" else InstanceNorm(irreps) if method == "instance" else None
 
     def forward(self, x, batch):
-        return self.n(x) if self.method == "batch" else x
+        if self.method == "batch":
+            return self.n(x)
+        if self.method == "instance":
+            return self.n(x, batch)
+        return x
+
+
+class MeanNormNormalize(torch.nn.Module):
+    """reference src/matten/data/transform.py:59-216 (the usable ``reduce="mean"`` branch; ``max`` raises there)."""
+
+    def __init__(self, irreps, mean=None, norm=None, normalization="component", reduce="mean", eps=1e-5, scale=1.0):
+        super().__init__()
+        self.irreps = E.parse_irreps(irreps)
+        self.normalization, self.reduce, self.eps, self.scale = normalization, reduce, eps, scale
+        self.mean, self.norm = mean, norm
+
+    def forward(self, data):
+        if self.mean is None or self.norm is None:
+            raise RuntimeError("mean and norm not initialized.")
+        return (data - self.mean) / (self.norm * self.scale)
+
+    def inverse(self, data):
+        if self.mean is None or self.norm is None:
+            raise RuntimeError("mean and norm not initialized.")
+        return data * (self.norm * self.scale) + self.mean
+
+    def compute_statistics(self, data):
+        all_mean, all_norm = [], []
+        ix = 0
+        for m, l, p in self.irreps:
+            d = 2 * l + 1
+            field = data[:, ix:ix + m * d].reshape(-1, m, d)
+            ix += m * d
+            if l == 0 and p == 1:
+                fm = field.mean(0).reshape(m)
+                field = field - fm.reshape(-1, m, 1)
+            else:
+                fm = torch.zeros(m, dtype=data.dtype)
+            all_mean.append(torch.repeat_interleave(fm, d))
+            fn = field.pow(2).sum(-1) if self.normalization == "norm" else field.pow(2).mean(-1)
+            assert self.reduce == "mean"
+            fn = (fn.mean(0) + self.eps).pow(0.5)
+            all_norm.append(torch.repeat_interleave(fn, d))
+        assert ix == data.shape[-1]
+        self.mean, self.norm = torch.cat(all_mean), torch.cat(all_norm)
+        return self.mean, self.norm
+
+
+class ScalarNormalize(MeanNormNormalize):
+    """reference src/matten/data/transform.py:219-302; sklearn StandardScaler.fit = column mean and population
+    standard deviation, deviations below 10 eps replaced by 1 (sklearn ``_handle_zeros_in_scale``)."""
+
+    def __init__(self, num_features, mean=None, norm=None, scale=1.0):
+        torch.nn.Module.__init__(self)
+        self.scale, self.mean, self.norm = scale, mean, norm
+
+    def compute_statistics(self, data):
+        assert data.ndim == 2, "Can only deal with tensor [N_samples, N_features]"
+        x = data.double()
+        mean = x.mean(0)
+        std = ((x - mean) ** 2).mean(0).sqrt()
+        std = torch.where(std < 10 * torch.finfo(torch.float64).eps, torch.ones_like(std), std)
+        self.mean, self.norm = mean.to(data.dtype), std.to(data.dtype)
+        return self.mean, self.norm
 
 
 class PointConvWithActivation(torch.nn.Module):
