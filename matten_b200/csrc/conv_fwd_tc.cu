@@ -158,10 +158,13 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
     }
     // (2) hidden layers of the radial MLP + sh pair rows, per padded column
     {
-      int64_t g = ceil_div<int64_t>(W.cols_max, 64);
+      const bool fast = p.nl == 3 && p.sizes[0] <= 8 && p.sizes[1] == kTcK && p.sizes[2] == kTcK &&
+                        p.act == MT_ACT_SILU;
+      int64_t g = ceil_div<int64_t>(W.cols_max, fast ? 256 : 64);
       if (g > (int64_t)kNumSMs * 8) g = (int64_t)kNumSMs * 8;
       if (g < 1) g = 1;
-      tc_edge_hidden_kernel<<<(unsigned)g, kHidThreads, 0, st>>>(p);
+      if (fast) tc_edge_hidden_fast_kernel<<<(unsigned)g, 256, 0, st>>>(p);
+      else tc_edge_hidden_kernel<<<(unsigned)g, kHidThreads, 0, st>>>(p);
       MT_LAUNCH_OK();
     }
   }

@@ -652,6 +652,100 @@ __global__ void __launch_bounds__(kHidThreads) tc_edge_hidden_kernel(const ConvT
   }
 }
 
+// The same stage for the MLP shape every matten config uses (n_rad <= 8 -> 32 -> 32 -> W, silu): lane == column, all
+// 32 hidden outputs of the column in registers, weights by warp-wide broadcast LDS.128.  Per input channel a lane
+// issues 8 LDS.128 and 16 FFMA2 and nothing else (the generic kernel above spends 40 % of its instructions on
+// predicates, index arithmetic and the shared-memory exchange between its four lanes per column: ncu r2_step_full).
+__global__ void __launch_bounds__(256) tc_edge_hidden_fast_kernel(const ConvTcParams p) {
+  __shared__ __align__(16) float sW0[8 * kTcK];
+  __shared__ __align__(16) float sW1[kTcK * kTcK];
+  const int in0 = p.sizes[0];
+  {
+    const float s0 = rsqrtf((float)in0), s1 = rsqrtf((float)kTcK);
+    for (int t = threadIdx.x; t < 8 * kTcK; t += 256) sW0[t] = (t >> 5) < in0 ? p.w[0][t] * s0 : 0.f;
+    for (int t = threadIdx.x; t < kTcK * kTcK; t += 256) sW1[t] = p.w[1][t] * s1;
+  }
+  __syncthreads();
+  const int yn = p.y_dim, ylmax = p.y_lmax;
+  const int ystride = 2 * sh_pad_len(ylmax);
+  const int64_t cols = p.rowptr_pad[p.N];
+  uint4* planes = reinterpret_cast<uint4*>(p.hplanes);
+  const float cst = p.act_cst;
+  const bool emb_vec = in0 == 8 && (reinterpret_cast<uintptr_t>(p.emb) & 15) == 0;
+  for (int64_t c = blockIdx.x * 256ll + threadIdx.x; c < cols; c += (int64_t)gridDim.x * 256) {
+    const int oe = p.orig_pad[c];
+    const bool real = oe >= 0;
+    const int64_t orig = real ? oe : (-1 - oe);
+    {  // sh components -> pair-interleaved padded row: degree-l block at position sh_pad_pos(l)
+      const float* __restrict__ yr = p.sh + orig * yn;
+      float* yo = p.ypairs + (c >> 1) * ystride + (c & 1);
+#pragma unroll
+      for (int l = 0; l <= MT_LMAX; ++l) {
+        if (l <= ylmax) {
+#pragma unroll
+          for (int k = 0; k < 2 * l + 1; ++k) yo[2 * (sh_pad_pos(l) + k)] = yr[l * l + k];
+        }
+      }
+    }
+    float h0[8];
+    if (emb_vec) {
+      const float4* er = reinterpret_cast<const float4*>(p.emb + orig * 8);
+      const float4 a = er[0], b = er[1];
+      h0[0] = a.x; h0[1] = a.y; h0[2] = a.z; h0[3] = a.w;
+      h0[4] = b.x; h0[5] = b.y; h0[6] = b.z; h0[7] = b.w;
+    } else {
+      const float* er = p.emb + orig * in0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h0[i] = i < in0 ? er[i] : 0.f;
+    }
+    float2 acc[16];
+    float h1[kTcK];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4* wr = reinterpret_cast<const float4*>(sW0 + k * kTcK);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w = wr[j];
+        fma_pair(h0[k], w.x, w.y, acc[2 * j]);
+        fma_pair(h0[k], w.z, w.w, acc[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      h1[2 * i] = acc[i].x * tc_fast_sigmoid(acc[i].x) * cst;
+      h1[2 * i + 1] = acc[i].y * tc_fast_sigmoid(acc[i].y) * cst;
+      acc[i] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kTcK; ++k) {
+      const float4* wr = reinterpret_cast<const float4*>(sW1 + k * kTcK);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w = wr[j];
+        fma_pair(h1[k], w.x, w.y, acc[2 * j]);
+        fma_pair(h1[k], w.z, w.w, acc[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float h8[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = acc[4 * g + i].x, b = acc[4 * g + i].y;
+        h8[2 * i] = real ? a * tc_fast_sigmoid(a) * cst : 0.f;  // pad column: zero weights
+        h8[2 * i + 1] = real ? b * tc_fast_sigmoid(b) * cst : 0.f;
+      }
+      uint4 hi, mi, lo;
+      tc_split8(h8, hi, mi, lo);
+      planes[(size_t)(0 * 4 + g) * p.cols_max + c] = hi;  // k-group g of the column
+      planes[(size_t)(1 * 4 + g) * p.cols_max + c] = mi;
+      planes[(size_t)(2 * 4 + g) * p.cols_max + c] = lo;
+    }
+  }
+}
+
 // =====================================================================================================
 // the kernel.  LMAXK: largest degree of the bundles compiled in (2: l <= 2 layers, 4: everything)
 // =====================================================================================================

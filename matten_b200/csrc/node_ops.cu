@@ -14,12 +14,17 @@ namespace mt {
 //   weight slice staged in shared memory (register-tiled 4x4 FMA micro-kernel).
 // =========================================================================
 constexpr int kLinMaxBlocks = 24;
-constexpr int kLinOut = 4096;    // outputs per CTA tile: rows x cols, 256 threads x (4 x 4)
-constexpr int kLinStage = 8192;  // staged x elements per k-chunk (rows x KC)
+constexpr int kLinStage = 4096;  // x elements staged per k-chunk: ROWS x KC
 constexpr int kLinMaxRows = 1024;
-// shared memory (elements of T): max over the tile shapes of staging (KC x (rows + 4) + KC x cols) and of the
-// output tile (rows x (cols + 1)) that aliases it
-constexpr int kLinSmemElems = 8832;
+constexpr int kLinMaxDim = 9;    // 2l+1 for l <= 4 takes the fast tables; larger dims fall back to divisions
+// Tile shapes (256 threads, thread tile TM rows x 4 columns):
+//   COLS  TM  ROWS  KC     stage elems 2 x (KC x (ROWS+4) + KC x COLS)     output tile ROWS x (COLS+1)
+//    64    8   128  32     12544                                            8320
+//    32    8   256  16      9344                                            8448
+//    16    8   512   8      8512                                            8704
+//     8    4   512   8      8384                                            4608
+//     4    4  1024   4      8256                                            5120
+constexpr int kLinSmemElems = 12544;
 
 template <typename T>
 __device__ __forceinline__ void lin_ld4(const T* p, T (&v)[4]);
@@ -35,6 +40,20 @@ __device__ __forceinline__ void lin_ld4<double>(const double* p, double (&v)[4])
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
+// one element global -> shared without passing through registers (LDGSTS); !valid zero-fills the destination
+template <typename T>
+__device__ __forceinline__ void lin_cp_async(T* smem_dst, const T* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? (int)sizeof(T) : 0;
+  if constexpr (sizeof(T) == 4)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void lin_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void lin_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct LinParams {
   int num_blocks;
   int32_t in_off[kLinMaxBlocks], out_off[kLinMaxBlocks], mul_in[kLinMaxBlocks], mul_out[kLinMaxBlocks],
@@ -43,7 +62,7 @@ struct LinParams {
   int32_t cta_begin[kLinMaxBlocks + 1];  // prefix of CTA counts per block
   int32_t col_chunks[kLinMaxBlocks];     // ceil(mul_out / cols)
   int32_t nodes_per_tile[kLinMaxBlocks];
-  int32_t tile_cols[kLinMaxBlocks];      // 64 / 32 / 16 / 8 / 4: the tile is (4096 / cols) rows x cols
+  int32_t tile_cols[kLinMaxBlocks];      // 64 / 32 / 16 / 8 / 4
   int in_dim, out_dim, S;
   const void* x;
   const void* weight;
@@ -55,13 +74,114 @@ struct LinParams {
   int64_t N;
 };
 
-// Tile shape per block: narrow outputs (mul_out = 4 for the l = 2 irreps, 16 for l = 1) take tall tiles, so the
-// 4 x 4 register micro-kernel never multiplies padding (a fixed 64 x 64 tile spent 97 % of its instructions on
-// it for the l >= 1 blocks of lin2: ncu r1, 330 M instructions for 18 M useful FMAs).
+struct LinTile {
+  int b, s, c0, ncols, tn, mi, mo, d, COLS, lc, ROWS, KC, XS;
+};
+
+// k loop + epilogue of one tile with a TM x 4 register tile per thread.  The k-chunks are double buffered in shared
+// memory and filled by cp.async one chunk ahead (round 1's kernel staged through registers with an integer division
+// per element and exposed the global latency: ncu r2_step_full, 38 % ALU pipe, 45 % long-scoreboard stalls, 8 % of
+// the instructions useful FMAs).  All index arithmetic in the loops is additive; the two (q / d, q % d) maps come from
+// tables filled once per CTA.
+template <typename T, int TM>
+__device__ __forceinline__ void lin_tile_run(const LinParams& p, const LinTile& t, T* smem, const int* s_nodes,
+                                             const int* qmap, const int* omap) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int COLS = t.COLS, KC = t.KC, XS = t.XS, d = t.d, mi = t.mi;
+  const int stage_elems = KC * XS + KC * COLS;
+  const T* __restrict__ X = static_cast<const T*>(p.x);
+  const T* __restrict__ W = static_cast<const T*>(p.weight);
+  T* __restrict__ OUT = static_cast<T*>(p.out);
+  const int tcn = COLS >> 2;
+  const int tc = tid % tcn, tr = tid / tcn;
+  using P = typename pair_of<T>::type;  // column pairs: one FFMA2 per pair in fp32
+  P acc[TM][2];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { acc[i][j].x = T(0); acc[i][j].y = T(0); }
+
+  const int nchunks = (mi + KC - 1) / KC;
+  const int kcd = KC * d;
+  auto issue = [&](int c) {
+    T* xsT = smem + (size_t)(c & 1) * stage_elems;  // [KC][XS]
+    T* ws = xsT + KC * XS;                          // [KC][COLS]
+    const int u0 = c * KC;
+    const int ku = min(KC, mi - u0);
+    const int seg = ku * d;
+    // x rows: warps over nodes, lanes over the node's contiguous [u0 * d, (u0 + KC) * d) segment (coalesced)
+    for (int j = warp; j < t.tn; j += 8) {
+      const T* src = X + (size_t)s_nodes[j] * p.in_dim + p.in_off[t.b] + u0 * d;
+      T* dst = xsT + j * d;
+      for (int q = lane; q < kcd; q += 32) lin_cp_async<T>(dst + qmap[q], src + (q < seg ? q : 0), q < seg);
+    }
+    // weight slice ws[uu][c] = W[w_off + ((u0+uu)*S + s)*mo + c0 + c]  (transposed: roles of u and c swapped)
+    for (int e = tid; e < KC * COLS; e += 256) {
+      const int uu = e >> t.lc, c = e & (COLS - 1);
+      const bool ok = uu < ku && c < t.ncols;
+      const size_t off = p.transpose ? (size_t)p.w_off[t.b] + ((size_t)(t.c0 + c) * p.S + t.s) * mi + (u0 + uu)
+                                     : (size_t)p.w_off[t.b] + ((size_t)(u0 + uu) * p.S + t.s) * t.mo + t.c0 + c;
+      lin_cp_async<T>(ws + e, W + (ok ? off : 0), ok);
+    }
+    lin_cp_commit();
+  };
+
+  issue(0);
+  for (int c = 0; c < nchunks; ++c) {
+    if (c + 1 < nchunks) {
+      issue(c + 1);
+      lin_cp_wait<1>();
+    } else {
+      lin_cp_wait<0>();
+    }
+    __syncthreads();
+    const T* xsT = smem + (size_t)(c & 1) * stage_elems;
+    const T* ws = xsT + KC * XS;
+    const T* ap = xsT + tr * TM;
+    const T* bp = ws + tc * 4;
+#pragma unroll 4
+    for (int uu = 0; uu < KC; ++uu) {
+      T a[TM], bb[4];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) lin_ld4<T>(ap + uu * XS + i, *reinterpret_cast<T(*)[4]>(&a[i]));
+      lin_ld4<T>(bp + uu * COLS, bb);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        fma_pair(a[i], bb[0], bb[1], acc[i][0]);
+        fma_pair(a[i], bb[2], bb[3], acc[i][1]);
+      }
+    }
+    __syncthreads();  // the buffer is refilled two chunks later
+  }
+  const T scale = T(p.scale[t.b]);
+  const int OS = COLS + 1;
+  T* ot = smem;  // [ROWS][COLS + 1], aliases the stages (all reads are behind the barrier above)
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      ot[(tr * TM + i) * OS + tc * 4 + 2 * j] = acc[i][j].x * scale;
+      ot[(tr * TM + i) * OS + tc * 4 + 2 * j + 1] = acc[i][j].y * scale;
+    }
+  __syncthreads();
+  // coalesced write: per node the (w, m) range is contiguous
+  const int span = t.ncols * d;
+  for (int j = warp; j < t.tn; j += 8) {
+    T* dst = OUT + (size_t)s_nodes[j] * p.out_dim + p.out_off[t.b] + t.c0 * d;
+    const T* src = ot + j * d * OS;
+    for (int q = lane; q < span; q += 32) {
+      const T v = src[omap[q]];
+      dst[q] = p.accumulate ? (dst[q] + v) : v;
+    }
+  }
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
+__global__ void __launch_bounds__(256, 2) linear_fwd_kernel(const LinParams p) {
   extern __shared__ __align__(16) unsigned char lin_smem[];
   __shared__ int s_nodes[kLinMaxRows];
+  __shared__ int s_qmap[32 * kLinMaxDim];  // q -> (q / d) * XS + q % d        (x staging, q < KC * d)
+  __shared__ int s_omap[64 * kLinMaxDim];  // q -> (q % d) * (COLS + 1) + q / d (output, q < ncols * d)
 
   // which block / node tile / column chunk am I?
   int b = 0;
@@ -70,13 +190,15 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
   const int cc = local % p.col_chunks[b];
   int tile = local / p.col_chunks[b];
   const int TN = p.nodes_per_tile[b];
-  const int mi = p.mul_in[b], mo = p.mul_out[b], d = p.dim[b];
-  const int COLS = p.tile_cols[b], ROWS = kLinOut / COLS;
-  const int KC = min(32, kLinStage / ROWS);
-  const int XS = ROWS + 4;  // row stride of the transposed x stage
-  T* xsT = reinterpret_cast<T*>(lin_smem);              // [KC][XS]
-  T* ws = xsT + (size_t)KC * XS;                        // [KC][COLS]
-  T* ot = reinterpret_cast<T*>(lin_smem);               // [ROWS][COLS + 1], aliases the stage after the k loop
+  LinTile t;
+  t.b = b;
+  t.mi = p.mul_in[b]; t.mo = p.mul_out[b]; t.d = p.dim[b];
+  t.COLS = p.tile_cols[b];
+  t.lc = 31 - __clz(t.COLS);
+  const int TM = t.COLS >= 16 ? 8 : 4;
+  t.ROWS = (256 / (t.COLS >> 2)) * TM;
+  t.KC = kLinStage / t.ROWS;
+  t.XS = t.ROWS + 4;  // row stride of the transposed x stage
   // locate (species, tile-in-species)
   int s = 0;
   int64_t begin = 0, end = 0;
@@ -99,93 +221,216 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinParams p) {
     }
     if (!found) return;
   }
-  const int tn = (int)(end - begin);
+  t.s = s;
+  t.tn = (int)(end - begin);
+  t.c0 = cc * t.COLS;
+  t.ncols = min(t.COLS, t.mo - t.c0);
   const int tid = threadIdx.x;
-  for (int t = tid; t < tn; t += blockDim.x) s_nodes[t] = p.sperm ? p.sperm[begin + t] : (int)(begin + t);
+  const int d = t.d;
+  for (int i = tid; i < t.tn; i += blockDim.x) s_nodes[i] = p.sperm ? p.sperm[begin + i] : (int)(begin + i);
+  for (int q = tid; q < t.KC * d; q += blockDim.x) s_qmap[q] = (q / d) * t.XS + q % d;
+  for (int q = tid; q < t.ncols * d; q += blockDim.x) s_omap[q] = (q % d) * (t.COLS + 1) + q / d;
   __syncthreads();
 
-  const T* __restrict__ X = static_cast<const T*>(p.x);
-  const T* __restrict__ W = static_cast<const T*>(p.weight);
-  T* __restrict__ OUT = static_cast<T*>(p.out);
-  const int c0 = cc * COLS;
-  const int ncols = min(COLS, mo - c0);
-
-  if (mi == 0) {  // irreps with no incoming path: zeros
+  if (t.mi == 0) {  // irreps with no incoming path: zeros
     if (!p.accumulate) {
-      for (int t = tid; t < tn * ncols * d; t += blockDim.x) {
-        int j = t / (ncols * d), q = t - j * (ncols * d);
-        OUT[(size_t)s_nodes[j] * p.out_dim + p.out_off[b] + c0 * d + q] = T(0);
-      }
+      T* __restrict__ OUT = static_cast<T*>(p.out);
+      const int span = t.ncols * d;
+      for (int j = tid >> 5; j < t.tn; j += 8)
+        for (int q = tid & 31; q < span; q += 32)
+          OUT[(size_t)s_nodes[j] * p.out_dim + p.out_off[b] + t.c0 * d + q] = T(0);
     }
     return;
   }
+  T* smem = reinterpret_cast<T*>(lin_smem);
+  if (TM == 8) lin_tile_run<T, 8>(p, t, smem, s_nodes, s_qmap, s_omap);
+  else lin_tile_run<T, 4>(p, t, smem, s_nodes, s_qmap, s_omap);
+}
 
-  const int tcn = COLS >> 2;  // thread columns
-  const int tc = tid % tcn, tr = tid / tcn;
-  using P = typename pair_of<T>::type;  // column pairs: one FFMA2 per pair in fp32
-  P acc[4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) { acc[i][j].x = T(0); acc[i][j].y = T(0); }
+// =========================================================================
+// Node-streaming linear: one CTA owns a tile of nodes of ONE species and walks ALL irrep blocks over it.
+//   * the species' weight slices of every block sit in shared memory for the CTA's lifetime;
+//   * each block's input columns of the tile's rows arrive by cp.async (16 B per lane, coalesced along the row), one
+//     block ahead of the arithmetic, so x is read from HBM exactly once and never passes through registers;
+//   * lanes <-> output channels w, NB nodes per lane in registers: per 4 input channels a lane issues 4 LDS.32 of
+//     weights (conflict free), NB x D LDS.128 of x (warp-wide broadcast) and NB x 4 x D FMAs.
+// The tiled kernel above spends 152 k thread instructions per node on lin2 of the last layer for 14.8 k MACs (rows
+// of 1392 floats cut into 80-byte slivers per k-chunk, every chunk paying the DRAM latency): ncu r2_step_full.
+// =========================================================================
+constexpr int kStreamSmemBytes = 200 * 1024;
 
-  for (int u0 = 0; u0 < mi; u0 += KC) {
-    const int ku = min(KC, mi - u0);
-    // stage weights  ws[uu][c] = W[w_off + ((u0+uu)*S + s)*mo + c0 + c]
-    for (int t = tid; t < KC * COLS; t += blockDim.x) {
-      int uu = t / COLS, c = t - uu * COLS;
-      T v = T(0);
-      if (uu < ku && c < ncols)
-        v = p.transpose ? W[(size_t)p.w_off[b] + ((size_t)(c0 + c) * p.S + s) * mi + (u0 + uu)]
-                        : W[(size_t)p.w_off[b] + ((size_t)(u0 + uu) * p.S + s) * mo + c0 + c];
-      ws[t] = v;
-    }
-    // stage x transposed  xsT[uu][j*d+m] = X[node_j, in_off + (u0+uu)*d + m]; rows beyond tn*d and uu >= ku are zero
-    const int seg = ku * d;
-    const int R = tn * d;
-    if (ku < KC || R < ROWS) {  // partial chunk / tile only: the staging below overwrites everything else
-      for (int t = tid; t < KC * ROWS; t += blockDim.x) {
-        const int uu = t / ROWS, r = t - uu * ROWS;
-        if (uu >= ku || r >= R) xsT[uu * XS + r] = T(0);
+struct LinStream {
+  int tnode;                        // nodes per CTA tile
+  int rs;                           // row stride (elements) of the staged x rows: max over blocks, multiple of 4, + 4
+  int w_smem_off[kLinMaxBlocks];    // element offset of block b's [mi4][mo] slice
+  int w_total;                      // elements of all slices
+  int vec_ok[kLinMaxBlocks];        // rows of this block can be copied 16 bytes at a time
+};
+
+// Lanes of a warp = (output channel w: lpn lanes) x (k-split ks: 32 / lpn lanes): every warp works on NB nodes
+// whatever mul_out is; narrow outputs (mul_out 16 or 4 for l >= 1) split the input channels over the spare lanes and
+// reduce with shuffles at the end.
+template <typename T, int D, int NB>
+__device__ __forceinline__ void lin_stream_block(const T* __restrict__ ws, const T* __restrict__ xs, int RS, int mi4,
+                                                 int mo, int tn, const int* __restrict__ s_nodes,
+                                                 T* __restrict__ OUT, int out_dim, int out_off, T scale,
+                                                 int accumulate) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int lpn = 32;  // lanes per channel group: the smallest of 32/16/8/4 covering mul_out (32 when mul_out > 16)
+  while (lpn > 4 && (lpn >> 1) >= mo) lpn >>= 1;
+  const int subs = 32 / lpn, ks = lane / lpn, wl = lane - ks * lpn;
+  for (int w0 = 0; w0 < mo; w0 += lpn) {
+    const int w = w0 + wl;
+    const bool wok = w < mo;
+    const T* wp = ws + (wok ? w : 0);
+    for (int n0 = warp * NB; n0 < tn; n0 += 8 * NB) {
+      T acc[NB][D];
+      const T* xr[NB];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+        for (int m = 0; m < D; ++m) acc[nb][m] = T(0);
+        xr[nb] = xs + (size_t)min(n0 + nb, tn - 1) * RS;  // rows past the tile repeat the last one; never stored
+      }
+      for (int u = ks * 4; u < mi4; u += 4 * subs) {
+        T wv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) wv[k] = wp[(u + k) * mo];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          T xv[4 * D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) lin_ld4<T>(xr[nb] + u * D + 4 * i, *reinterpret_cast<T(*)[4]>(&xv[4 * i]));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int m = 0; m < D; ++m) acc[nb][m] = fma(wv[k], xv[k * D + m], acc[nb][m]);
+        }
+      }
+      for (int off = lpn; off < 32; off <<= 1) {  // sum the k-splits (fixed order: deterministic)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int m = 0; m < D; ++m) acc[nb][m] += __shfl_xor_sync(0xffffffffu, acc[nb][m], off);
+      }
+      if (wok && ks == 0) {
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          if (n0 + nb < tn) {
+            T* dst = OUT + (size_t)s_nodes[n0 + nb] * out_dim + out_off + w * D;
+#pragma unroll
+            for (int m = 0; m < D; ++m) dst[m] = accumulate ? (dst[m] + acc[nb][m] * scale) : acc[nb][m] * scale;
+          }
+        }
       }
     }
-    for (int t = tid; t < tn * seg; t += blockDim.x) {
-      int j = t / seg, q = t - j * seg;
-      int uu = q / d, m = q - uu * d;
-      xsT[uu * XS + j * d + m] = X[(size_t)s_nodes[j] * p.in_dim + p.in_off[b] + u0 * d + q];
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int uu = 0; uu < KC; ++uu) {
-      T a[4], bb[4];
-      lin_ld4<T>(xsT + uu * XS + tr * 4, a);   // 16-byte aligned: XS and COLS are multiples of 4
-      lin_ld4<T>(ws + uu * COLS + tc * 4, bb);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        fma_pair(a[i], bb[0], bb[1], acc[i][0]);
-        fma_pair(a[i], bb[2], bb[3], acc[i][1]);
-      }
-    }
-    __syncthreads();
   }
-  const T scale = T(p.scale[b]);
-  const int OS = COLS + 1;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      ot[(tr * 4 + i) * OS + tc * 4 + 2 * j] = acc[i][j].x * scale;
-      ot[(tr * 4 + i) * OS + tc * 4 + 2 * j + 1] = acc[i][j].y * scale;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) linear_stream_kernel(const LinParams p, const LinStream e) {
+  extern __shared__ __align__(16) unsigned char lin_smem[];
+  __shared__ int s_nodes[64];
+  T* wsm = reinterpret_cast<T*>(lin_smem);
+  T* xbuf = wsm + ((e.w_total + 3) & ~3);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // locate (species, tile-in-species)
+  int tile = blockIdx.x, s = 0;
+  int64_t begin = 0, end = 0;
+  if (p.S == 1 && p.sptr == nullptr) {
+    begin = (int64_t)tile * e.tnode;
+    end = imin64(begin + e.tnode, p.N);
+    if (begin >= p.N) return;
+  } else {
+    bool found = false;
+    for (s = 0; s < p.S; ++s) {
+      const int cnt = p.sptr[s + 1] - p.sptr[s];
+      const int nt = (cnt + e.tnode - 1) / e.tnode;
+      if (tile < nt) {
+        begin = p.sptr[s] + (int64_t)tile * e.tnode;
+        end = imin64(begin + e.tnode, (int64_t)p.sptr[s + 1]);
+        found = true;
+        break;
+      }
+      tile -= nt;
     }
-  __syncthreads();
-  // coalesced write: per node the (w, m) range is contiguous
-  const int span = ncols * d;
-  for (int t = tid; t < tn * span; t += blockDim.x) {
-    int j = t / span, q = t - j * span;
-    int w = q / d, m = q - w * d;
-    size_t o = (size_t)s_nodes[j] * p.out_dim + p.out_off[b] + c0 * d + q;
-    T v = ot[(j * d + m) * OS + w];
-    OUT[o] = p.accumulate ? (OUT[o] + v) : v;
+    if (!found) return;
+  }
+  const int tn = (int)(end - begin);
+  if (tid < tn) s_nodes[tid] = p.sperm ? p.sperm[begin + tid] : (int)(begin + tid);
+  const T* __restrict__ X = static_cast<const T*>(p.x);
+  const T* __restrict__ W = static_cast<const T*>(p.weight);
+  T* __restrict__ OUT = static_cast<T*>(p.out);
+  // this species' weight slices, [mi4][mo] per block (rows mi..mi4 zero): warps over u, lanes over w; asynchronous
+  // copies, all in flight at once (the first group the pipeline below waits for)
+  for (int b = 0; b < p.num_blocks; ++b) {
+    const int mi = p.mul_in[b], mo = p.mul_out[b], mi4 = (mi + 3) & ~3;
+    T* dst = wsm + e.w_smem_off[b];
+    for (int u = warp; u < mi4; u += 8)
+      for (int w = lane; w < mo; w += 32) {
+        const bool ok = u < mi;
+        const size_t off = !ok ? 0
+                           : p.transpose ? (size_t)p.w_off[b] + ((size_t)w * p.S + s) * mi + u
+                                         : (size_t)p.w_off[b] + ((size_t)u * p.S + s) * mo + w;
+        lin_cp_async<T>(dst + u * mo + w, W + off, ok);
+      }
+  }
+  lin_cp_commit();
+  __syncthreads();  // s_nodes
+  constexpr int V = 16 / (int)sizeof(T);  // elements per 16-byte copy
+  auto issue = [&](int b) {
+    const int mi = p.mul_in[b], d = p.dim[b];
+    const int seg = mi * d, segp = (((mi + 3) & ~3) * d + 3) & ~3;  // copied + zero-filled up to the padded length
+    T* buf = xbuf + (size_t)(b & 1) * e.tnode * e.rs;
+    if (mi > 0) {
+      for (int j = warp; j < tn; j += 8) {
+        const T* src = X + (size_t)s_nodes[j] * p.in_dim + p.in_off[b];
+        T* dst = buf + (size_t)j * e.rs;
+        if (e.vec_ok[b]) {
+          for (int q = lane * V; q < segp; q += 32 * V) {
+            const int n = min(V, seg - q);  // elements really there
+            const uint32_t da = (uint32_t)__cvta_generic_to_shared(dst + q);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(src + (n > 0 ? q : 0)),
+                         "r"(n > 0 ? n * (int)sizeof(T) : 0)
+                         : "memory");
+          }
+        } else {
+          for (int q = lane; q < segp; q += 32) lin_cp_async<T>(dst + q, src + (q < seg ? q : 0), q < seg);
+        }
+      }
+    }
+    lin_cp_commit();
+  };
+  issue(0);
+  for (int b = 0; b < p.num_blocks; ++b) {
+    if (b + 1 < p.num_blocks) {
+      issue(b + 1);
+      lin_cp_wait<1>();
+    } else {
+      lin_cp_wait<0>();
+    }
+    __syncthreads();
+    const int mi = p.mul_in[b], mo = p.mul_out[b], d = p.dim[b];
+    const T* xs = xbuf + (size_t)(b & 1) * e.tnode * e.rs;
+    if (mi == 0) {
+      if (!p.accumulate) {
+        const int span = mo * d;
+        for (int j = warp; j < tn; j += 8)
+          for (int q = lane; q < span; q += 32) OUT[(size_t)s_nodes[j] * p.out_dim + p.out_off[b] + q] = T(0);
+      }
+    } else {
+      const T* ws = wsm + e.w_smem_off[b];
+      const int mi4 = (mi + 3) & ~3;
+      const T sc = T(p.scale[b]);
+      switch (d) {
+        case 1: lin_stream_block<T, 1, 4>(ws, xs, e.rs, mi4, mo, tn, s_nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate); break;
+        case 3: lin_stream_block<T, 3, 4>(ws, xs, e.rs, mi4, mo, tn, s_nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate); break;
+        case 5: lin_stream_block<T, 5, 2>(ws, xs, e.rs, mi4, mo, tn, s_nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate); break;
+        case 7: lin_stream_block<T, 7, 2>(ws, xs, e.rs, mi4, mo, tn, s_nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate); break;
+        default: lin_stream_block<T, 9, 1>(ws, xs, e.rs, mi4, mo, tn, s_nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate); break;
+      }
+    }
+    __syncthreads();  // the buffer is refilled by block b + 2
   }
 }
 
@@ -256,13 +501,60 @@ static int linear_fwd_round(int dtype, const mt_lin_block* const* blocks, int nu
   p.transpose = transpose;
   p.num_blocks = num_blocks;
   int64_t total = 0;
+  // ---- node-streaming kernel whenever the block dims are 2l+1 <= 9 and the tile fits in shared memory
+  {
+    LinStream e;
+    memset(&e, 0, sizeof(e));
+    const size_t es = dtype == MT_F64 ? 8 : 4;
+    const int V = 16 / (int)es;
+    bool ok = true;
+    int rs = 0;
+    for (int b = 0; b < num_blocks; ++b) {
+      const mt_lin_block& k = *blocks[b];
+      p.in_off[b] = k.in_off; p.out_off[b] = k.out_off; p.mul_in[b] = k.mul_in; p.mul_out[b] = k.mul_out;
+      p.dim[b] = k.dim; p.w_off[b] = k.w_off; p.scale[b] = k.scale;
+      if (!(k.dim == 1 || k.dim == 3 || k.dim == 5 || k.dim == 7 || k.dim == 9)) ok = false;
+      const int mi4 = (k.mul_in + 3) & ~3;
+      e.w_smem_off[b] = e.w_total;
+      e.w_total += mi4 * k.mul_out;
+      e.w_total = (e.w_total + 3) & ~3;
+      const int segp = (mi4 * k.dim + 3) & ~3;
+      if (segp > rs) rs = segp;
+      e.vec_ok[b] = (k.in_off % V == 0) && (in_dim % V == 0) && ((uintptr_t)x % 16 == 0);
+    }
+    e.rs = rs + 4;
+    int tnode = 32;
+    auto need = [&](int tn) { return ((size_t)((e.w_total + 3) & ~3) + 2 * (size_t)tn * e.rs) * es; };
+    // two resident CTAs per SM (16 warps, one CTA's copies under the other's arithmetic) beat one big tile
+    while (tnode > 8 && need(tnode) > (size_t)(kStreamSmemBytes / 2 - 8 * 1024)) tnode >>= 1;
+    if (ok && need(tnode) <= (size_t)kStreamSmemBytes) {
+      e.tnode = tnode;
+      p.in_dim = in_dim; p.out_dim = out_dim; p.S = num_species;
+      p.x = x; p.weight = weight; p.sperm = species_perm; p.sptr = species_ptr;
+      p.accumulate = accumulate; p.out = out; p.N = N;
+      const int64_t tiles = ceil_div<int64_t>(N, tnode) + (species_ptr ? num_species : 0);
+      MT_REQUIRE(tiles < (int64_t)2147483647, "grid too large");
+      const size_t smem = need(tnode);
+      MT_DISPATCH_DTYPE(dtype, {
+        static thread_local bool configured = false;
+        if (!configured) {
+          MT_CUDA_OK(cudaFuncSetAttribute(linear_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kStreamSmemBytes));
+          configured = true;
+        }
+        linear_stream_kernel<T><<<(unsigned)tiles, 256, smem, st>>>(p, e);
+      });
+      MT_LAUNCH_OK();
+      return MT_OK;
+    }
+  }
   for (int b = 0; b < num_blocks; ++b) {
     const mt_lin_block& k = *blocks[b];
     p.in_off[b] = k.in_off; p.out_off[b] = k.out_off; p.mul_in[b] = k.mul_in; p.mul_out[b] = k.mul_out;
     p.dim[b] = k.dim; p.w_off[b] = k.w_off; p.scale[b] = k.scale;
     int cols = 64;
     while (cols > 4 && cols / 2 >= k.mul_out) cols /= 2;  // smallest of 64/32/16/8/4 that covers mul_out (<= 64)
-    const int rows = kLinOut / cols;
+    const int rows = (256 / (cols / 4)) * (cols >= 16 ? 8 : 4);
     int tn = rows / k.dim;
     if (tn < 1) tn = 1;
     p.tile_cols[b] = cols;
@@ -294,7 +586,7 @@ static int linear_check_blocks(const mt_lin_block* blocks, int num_blocks, int i
                                const void* weight) {
   for (int b = 0; b < num_blocks; ++b) {
     const mt_lin_block& k = blocks[b];
-    MT_REQUIRE(k.dim >= 1 && k.dim <= 64 && k.mul_out > 0 && k.mul_in >= 0, "bad linear block %d", b);
+    MT_REQUIRE(k.dim >= 1 && k.dim <= kLinMaxDim && k.mul_out > 0 && k.mul_in >= 0, "bad linear block %d", b);
     MT_REQUIRE(k.out_off >= 0 && k.out_off + k.mul_out * k.dim <= out_dim, "block %d exceeds out_dim", b);
     MT_REQUIRE(k.mul_in == 0 || (k.in_off >= 0 && k.in_off + k.mul_in * k.dim <= in_dim), "block %d exceeds in_dim", b);
     MT_REQUIRE(k.mul_in == 0 || weight != nullptr, "null weight");
