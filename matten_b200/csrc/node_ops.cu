@@ -265,6 +265,8 @@ struct LinStream {
   int w_smem_off[kLinMaxBlocks];    // element offset of block b's [mi4][mo] slice
   int w_total;                      // elements of all slices
   int vec_ok[kLinMaxBlocks];        // rows of this block can be copied 16 bytes at a time
+  int w_vec[kLinMaxBlocks];         // ... and so can the rows of its weight slice
+  int tiles_per_cta;                // consecutive tiles of one species per CTA (weights staged once for all of them)
 };
 
 // Lanes of a warp = (output channel w: lpn lanes) x (k-split ks: 32 / lpn lanes): every warp works on NB nodes
@@ -279,28 +281,32 @@ __device__ __forceinline__ void lin_stream_block(const T* __restrict__ ws, const
   int lpn = 32;  // lanes per channel group: the smallest of 32/16/8/4 covering mul_out (32 when mul_out > 16)
   while (lpn > 4 && (lpn >> 1) >= mo) lpn >>= 1;
   const int subs = 32 / lpn, ks = lane / lpn, wl = lane - ks * lpn;
+  const int ustep = 4 * subs;
   for (int w0 = 0; w0 < mo; w0 += lpn) {
     const int w = w0 + wl;
     const bool wok = w < mo;
-    const T* wp = ws + (wok ? w : 0);
     for (int n0 = warp * NB; n0 < tn; n0 += 8 * NB) {
       T acc[NB][D];
-      const T* xr[NB];
+      const T* xq[NB];
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
         for (int m = 0; m < D; ++m) acc[nb][m] = T(0);
-        xr[nb] = xs + (size_t)min(n0 + nb, tn - 1) * RS;  // rows past the tile repeat the last one; never stored
+        // rows past the tile repeat the last one; never stored
+        xq[nb] = xs + (size_t)min(n0 + nb, tn - 1) * RS + ks * 4 * D;
       }
-      for (int u = ks * 4; u < mi4; u += 4 * subs) {
+      const T* wq = ws + (wok ? w : 0) + ks * 4 * mo;
+      for (int u = ks * 4; u < mi4; u += ustep) {
         T wv[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) wv[k] = wp[(u + k) * mo];
+        for (int k = 0; k < 4; ++k) wv[k] = wq[k * mo];
+        wq += ustep * mo;
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
           T xv[4 * D];
 #pragma unroll
-          for (int i = 0; i < D; ++i) lin_ld4<T>(xr[nb] + u * D + 4 * i, *reinterpret_cast<T(*)[4]>(&xv[4 * i]));
+          for (int i = 0; i < D; ++i) lin_ld4<T>(xq[nb] + 4 * i, *reinterpret_cast<T(*)[4]>(&xv[4 * i]));
+          xq[nb] += ustep * D;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -327,28 +333,31 @@ __device__ __forceinline__ void lin_stream_block(const T* __restrict__ ws, const
   }
 }
 
+constexpr int kStreamTiles = 8;  // at most: consecutive tiles of one species per CTA (weight slices staged once)
+
 template <typename T>
 __global__ void __launch_bounds__(256) linear_stream_kernel(const LinParams p, const LinStream e) {
   extern __shared__ __align__(16) unsigned char lin_smem[];
-  __shared__ int s_nodes[64];
+  __shared__ int s_nodes[kStreamTiles * 32];
   T* wsm = reinterpret_cast<T*>(lin_smem);
   T* xbuf = wsm + ((e.w_total + 3) & ~3);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // locate (species, tile-in-species)
+  const int super = e.tnode * e.tiles_per_cta;
+  // locate (species, super-tile-in-species)
   int tile = blockIdx.x, s = 0;
   int64_t begin = 0, end = 0;
   if (p.S == 1 && p.sptr == nullptr) {
-    begin = (int64_t)tile * e.tnode;
-    end = imin64(begin + e.tnode, p.N);
+    begin = (int64_t)tile * super;
+    end = imin64(begin + super, p.N);
     if (begin >= p.N) return;
   } else {
     bool found = false;
     for (s = 0; s < p.S; ++s) {
       const int cnt = p.sptr[s + 1] - p.sptr[s];
-      const int nt = (cnt + e.tnode - 1) / e.tnode;
+      const int nt = (cnt + super - 1) / super;
       if (tile < nt) {
-        begin = p.sptr[s] + (int64_t)tile * e.tnode;
-        end = imin64(begin + e.tnode, (int64_t)p.sptr[s + 1]);
+        begin = p.sptr[s] + (int64_t)tile * super;
+        end = imin64(begin + super, (int64_t)p.sptr[s + 1]);
         found = true;
         break;
       }
@@ -356,45 +365,66 @@ __global__ void __launch_bounds__(256) linear_stream_kernel(const LinParams p, c
     }
     if (!found) return;
   }
-  const int tn = (int)(end - begin);
-  if (tid < tn) s_nodes[tid] = p.sperm ? p.sperm[begin + tid] : (int)(begin + tid);
+  const int tn_all = (int)(end - begin);
+  const int ntiles = (tn_all + e.tnode - 1) / e.tnode;
+  for (int i = tid; i < tn_all; i += 256) s_nodes[i] = p.sperm ? p.sperm[begin + i] : (int)(begin + i);
   const T* __restrict__ X = static_cast<const T*>(p.x);
   const T* __restrict__ W = static_cast<const T*>(p.weight);
   T* __restrict__ OUT = static_cast<T*>(p.out);
-  // this species' weight slices, [mi4][mo] per block (rows mi..mi4 zero): warps over u, lanes over w; asynchronous
-  // copies, all in flight at once (the first group the pipeline below waits for)
+  constexpr int V = 16 / (int)sizeof(T);  // elements per 16-byte copy
+  // this species' weight slices, [mi4][mo] per block (rows mi..mi4 zero); asynchronous copies, all in flight at once
+  // (the first group the pipeline below waits for).  Rows of mo contiguous elements: 16 bytes per copy when mo allows.
   for (int b = 0; b < p.num_blocks; ++b) {
     const int mi = p.mul_in[b], mo = p.mul_out[b], mi4 = (mi + 3) & ~3;
     T* dst = wsm + e.w_smem_off[b];
-    for (int u = warp; u < mi4; u += 8)
-      for (int w = lane; w < mo; w += 32) {
+    if (!p.transpose && e.w_vec[b]) {
+      const int rowv = mo / V;  // vectors per row
+      const int nvec = mi4 * rowv;
+      int u = tid / rowv, c = tid - u * rowv;          // one division per thread and block; then additive
+      const int du = 256 / rowv, dc = 256 - du * rowv;
+      for (int v = tid; v < nvec; v += 256) {
         const bool ok = u < mi;
-        const size_t off = !ok ? 0
-                           : p.transpose ? (size_t)p.w_off[b] + ((size_t)w * p.S + s) * mi + u
-                                         : (size_t)p.w_off[b] + ((size_t)u * p.S + s) * mo + w;
-        lin_cp_async<T>(dst + u * mo + w, W + off, ok);
+        const T* src = W + (ok ? (size_t)p.w_off[b] + ((size_t)u * p.S + s) * mo + c * V : 0);
+        const uint32_t da = (uint32_t)__cvta_generic_to_shared(dst + u * mo + c * V);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        u += du; c += dc;
+        if (c >= rowv) { c -= rowv; ++u; }
       }
+    } else {
+      for (int u = warp; u < mi4; u += 8)
+        for (int w = lane; w < mo; w += 32) {
+          const bool ok = u < mi;
+          const size_t off = !ok ? 0
+                             : p.transpose ? (size_t)p.w_off[b] + ((size_t)w * p.S + s) * mi + u
+                                           : (size_t)p.w_off[b] + ((size_t)u * p.S + s) * mo + w;
+          lin_cp_async<T>(dst + u * mo + w, W + off, ok);
+        }
+    }
   }
   lin_cp_commit();
   __syncthreads();  // s_nodes
-  constexpr int V = 16 / (int)sizeof(T);  // elements per 16-byte copy
-  auto issue = [&](int b) {
+  const int nb_ = p.num_blocks;
+  const int nsteps = ntiles * nb_;
+  const uint32_t xbuf_s = (uint32_t)__cvta_generic_to_shared(xbuf);
+  auto issue = [&](int step) {
+    const int t = step / nb_, b = step - t * nb_;
     const int mi = p.mul_in[b], d = p.dim[b];
     const int seg = mi * d, segp = (((mi + 3) & ~3) * d + 3) & ~3;  // copied + zero-filled up to the padded length
-    T* buf = xbuf + (size_t)(b & 1) * e.tnode * e.rs;
+    const int n0 = t * e.tnode, tn = min(e.tnode, tn_all - n0);
+    const uint32_t buf_s = xbuf_s + (uint32_t)((step & 1) * e.tnode * e.rs * (int)sizeof(T));
     if (mi > 0) {
       for (int j = warp; j < tn; j += 8) {
-        const T* src = X + (size_t)s_nodes[j] * p.in_dim + p.in_off[b];
-        T* dst = buf + (size_t)j * e.rs;
+        const T* src = X + (size_t)s_nodes[n0 + j] * p.in_dim + p.in_off[b];
+        const uint32_t drow = buf_s + (uint32_t)(j * e.rs * (int)sizeof(T));
         if (e.vec_ok[b]) {
           for (int q = lane * V; q < segp; q += 32 * V) {
             const int n = min(V, seg - q);  // elements really there
-            const uint32_t da = (uint32_t)__cvta_generic_to_shared(dst + q);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(src + (n > 0 ? q : 0)),
-                         "r"(n > 0 ? n * (int)sizeof(T) : 0)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(drow + q * (int)sizeof(T)),
+                         "l"(src + (n > 0 ? q : 0)), "r"(n > 0 ? n * (int)sizeof(T) : 0)
                          : "memory");
           }
         } else {
+          T* dst = xbuf + (size_t)(step & 1) * e.tnode * e.rs + (size_t)j * e.rs;
           for (int q = lane; q < segp; q += 32) lin_cp_async<T>(dst + q, src + (q < seg ? q : 0), q < seg);
         }
       }
@@ -402,35 +432,52 @@ __global__ void __launch_bounds__(256) linear_stream_kernel(const LinParams p, c
     lin_cp_commit();
   };
   issue(0);
-  for (int b = 0; b < p.num_blocks; ++b) {
-    if (b + 1 < p.num_blocks) {
-      issue(b + 1);
+  for (int step = 0; step < nsteps; ++step) {
+    if (step + 1 < nsteps) {
+      issue(step + 1);
       lin_cp_wait<1>();
     } else {
       lin_cp_wait<0>();
     }
     __syncthreads();
+    const int t = step / nb_, b = step - t * nb_;
+    const int n0 = t * e.tnode, tn = min(e.tnode, tn_all - n0);
     const int mi = p.mul_in[b], mo = p.mul_out[b], d = p.dim[b];
-    const T* xs = xbuf + (size_t)(b & 1) * e.tnode * e.rs;
+    const T* xs = xbuf + (size_t)(step & 1) * e.tnode * e.rs;
+    const int* nodes = s_nodes + n0;
     if (mi == 0) {
       if (!p.accumulate) {
         const int span = mo * d;
         for (int j = warp; j < tn; j += 8)
-          for (int q = lane; q < span; q += 32) OUT[(size_t)s_nodes[j] * p.out_dim + p.out_off[b] + q] = T(0);
+          for (int q = lane; q < span; q += 32) OUT[(size_t)nodes[j] * p.out_dim + p.out_off[b] + q] = T(0);
       }
     } else {
       const T* ws = wsm + e.w_smem_off[b];
       const int mi4 = (mi + 3) & ~3;
       const T sc = T(p.scale[b]);
-      switch (d) {
-        case 1: lin_stream_block<T, 1, 4>(ws, xs, e.rs, mi4, mo, tn, s_nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate); break;
-        case 3: lin_stream_block<T, 3, 4>(ws, xs, e.rs, mi4, mo, tn, s_nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate); break;
-        case 5: lin_stream_block<T, 5, 2>(ws, xs, e.rs, mi4, mo, tn, s_nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate); break;
-        case 7: lin_stream_block<T, 7, 2>(ws, xs, e.rs, mi4, mo, tn, s_nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate); break;
-        default: lin_stream_block<T, 9, 1>(ws, xs, e.rs, mi4, mo, tn, s_nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate); break;
+      // nodes per lane: 8 warps x NB covers the tile (NB = 4 for 32-node tiles, 2 for 16-node tiles), fewer for wide irreps
+#define MT_LIN_BLOCK(DD, NBB) \
+  lin_stream_block<T, DD, NBB>(ws, xs, e.rs, mi4, mo, tn, nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate)
+      if (e.tnode > 16) {
+        switch (d) {
+          case 1: MT_LIN_BLOCK(1, 4); break;
+          case 3: MT_LIN_BLOCK(3, 4); break;
+          case 5: MT_LIN_BLOCK(5, 2); break;
+          case 7: MT_LIN_BLOCK(7, 2); break;
+          default: MT_LIN_BLOCK(9, 1); break;
+        }
+      } else {
+        switch (d) {
+          case 1: MT_LIN_BLOCK(1, 2); break;
+          case 3: MT_LIN_BLOCK(3, 2); break;
+          case 5: MT_LIN_BLOCK(5, 2); break;
+          case 7: MT_LIN_BLOCK(7, 1); break;
+          default: MT_LIN_BLOCK(9, 1); break;
+        }
       }
+#undef MT_LIN_BLOCK
     }
-    __syncthreads();  // the buffer is refilled by block b + 2
+    __syncthreads();  // the buffer is refilled by step + 2
   }
 }
 
@@ -521,6 +568,7 @@ static int linear_fwd_round(int dtype, const mt_lin_block* const* blocks, int nu
       const int segp = (mi4 * k.dim + 3) & ~3;
       if (segp > rs) rs = segp;
       e.vec_ok[b] = (k.in_off % V == 0) && (in_dim % V == 0) && ((uintptr_t)x % 16 == 0);
+      e.w_vec[b] = (k.mul_out % V == 0) && (k.w_off % V == 0) && ((uintptr_t)weight % 16 == 0) && k.mul_out / V <= 256;
     }
     e.rs = rs + 4;
     int tnode = 32;
@@ -532,7 +580,11 @@ static int linear_fwd_round(int dtype, const mt_lin_block* const* blocks, int nu
       p.in_dim = in_dim; p.out_dim = out_dim; p.S = num_species;
       p.x = x; p.weight = weight; p.sperm = species_perm; p.sptr = species_ptr;
       p.accumulate = accumulate; p.out = out; p.N = N;
-      const int64_t tiles = ceil_div<int64_t>(N, tnode) + (species_ptr ? num_species : 0);
+      // several tiles per CTA only when that still leaves >= 4 CTAs per SM
+      int tpc = (int)(N / ((int64_t)tnode * 4 * kNumSMs));
+      tpc = tpc < 1 ? 1 : (tpc > kStreamTiles ? kStreamTiles : tpc);
+      e.tiles_per_cta = tpc;
+      const int64_t tiles = ceil_div<int64_t>(N, (int64_t)tnode * tpc) + (species_ptr ? num_species : 0);
       MT_REQUIRE(tiles < (int64_t)2147483647, "grid too large");
       const size_t smem = need(tnode);
       MT_DISPATCH_DTYPE(dtype, {

@@ -22,9 +22,14 @@ class CapturedForward:
         self.warmup = warmup
         self._graphs: Dict[Tuple, tuple] = {}
 
-    @staticmethod
-    def _signature(batch, slot: int = 0) -> Tuple:
-        return (slot,) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) if isinstance(v, torch.Tensor) else (k, v)
+    def _model_version(self) -> int:
+        """Changes whenever a parameter or buffer is written in place (optimizer step, load_state_dict): derived
+        vectors cached outside the graph (BatchNorm.eval_affine) would otherwise go stale inside a capture."""
+        return hash(tuple(t._version for t in self.model.parameters()) +
+                    tuple(t._version for t in self.model.buffers()))
+
+    def _signature(self, batch, slot: int = 0) -> Tuple:
+        return (slot, self._model_version()) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) if isinstance(v, torch.Tensor) else (k, v)
                                       for k, v in batch.items() if not k.startswith("_")))
 
     def _capture(self, batch):

@@ -299,7 +299,13 @@ class BatchNorm(_Buffers):
 
     def eval_affine(self, dtype):
         """Per-element (a, b) with ``y = a*x + b`` for eval mode: tiny [D] vectors derived from
-        the running statistics (parameter plumbing, not per-node work)."""
+        the running statistics (parameter plumbing, not per-node work).  Cached between calls while the parameters
+        and running statistics are unchanged (tensor version counters) -- ten small launches per layer otherwise."""
+        key = (dtype, self.feat_idx.device, self.weight._version, self.bias._version, self.running_mean._version,
+               self.running_var._version, self.weight.data_ptr(), self.running_var.data_ptr())
+        cached = getattr(self, "_affine_cache", None)
+        if cached is not None and cached[0] == key and not (torch.is_grad_enabled() and self.weight.requires_grad):
+            return cached[1]
         rstd = (self.running_var + self.eps).pow(-0.5) * self.weight
         a = rstd[self.feat_idx]
         if self.num_scalar > 0:
@@ -307,7 +313,10 @@ class BatchNorm(_Buffers):
             b = torch.where(self.scal_mask, shift[self.scal_idx], torch.zeros_like(a))
         else:
             b = torch.zeros_like(a)
-        return a.to(dtype).contiguous(), b.to(dtype).contiguous()
+        out = (a.to(dtype).contiguous(), b.to(dtype).contiguous())
+        if not (torch.is_grad_enabled() and self.weight.requires_grad):
+            self._affine_cache = (key, (out[0].detach(), out[1].detach()))
+        return out
 
     def _scalar_channels(self):
         if not hasattr(self, "_sc_cache") or self._sc_cache.device != self.feat_idx.device:
