@@ -249,8 +249,20 @@ size_t mt_conv_fwd_workspace_bytes(const mt_conv_plan* plan, int dtype, int64_t 
 int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* sh,
                 const void* emb, const void* const* mlp_weights, const int32_t* rowptr,
                 const int32_t* perm, const int32_t* src_sorted, double avg_num_neighbors,
-                const void* num_neigh, void* out, void* workspace, size_t workspace_bytes, int64_t N,
-                int64_t E, mt_stream stream);
+                const void* num_neigh, void* out, void* workspace, size_t workspace_bytes,
+                const void* layout, int64_t N, int64_t E, mt_stream stream);
+
+/* The layer-invariant inputs of the tcgen05 path: the padded column order of the receiver-sorted edge list and the
+ * pair-interleaved spherical-harmonics rows.  Every PointConv layer of a forward shares the graph and edge_sh
+ * (reference src/matten/model_factory/tfn_scalar_tensor.py:160-214: one spharm_edges module feeds all layers), so the
+ * caller prepares them ONCE per batch and passes the buffer as `layout` to every mt_conv_fwd of that batch
+ * (layout NULL: mt_conv_fwd rebuilds them in its workspace at every call).  fp32 only (the fp64 and FMA-pipe
+ * kernels ignore it); y_lmax is the largest degree of edge_sh, whose blocks must be 0 .. y_lmax in order.
+ * layout: mt_conv_layout_bytes(y_lmax, N, E) bytes, 256-byte aligned. */
+size_t mt_conv_layout_bytes(int y_lmax, int64_t N, int64_t E);
+int mt_conv_layout_prepare(int y_lmax, const void* sh, const int32_t* rowptr, const int32_t* perm,
+                           const int32_t* src_sorted, int64_t N, int64_t E, void* layout, size_t layout_bytes,
+                           mt_stream stream);
 
 /* Which fp32 kernel mt_conv_fwd uses: 0 = automatic (tcgen05 when the plan qualifies, else FMA pipes), 1 = tcgen05
  * only (MT_EINVAL when the plan does not qualify), 2 = FMA pipes only.  Process-wide; the initial value comes from

@@ -77,7 +77,9 @@ SIGNATURES = {
     "mt_species_embed": (_I, [_I, _V, _I, _V, _L, _L, _I, _I, _V, _V, _L, _V, _V, _V, _V, _V]),
     "mt_conv_fwd_workspace_bytes": (_Z, [C.POINTER(ConvPlanStruct), _I, _L, _L]),
     "mt_conv_fwd": (_I, [C.POINTER(ConvPlanStruct), _I, _V, _V, _V, C.POINTER(_V), _V, _V, _V, _D, _V, _V,
-                         _V, _Z, _L, _L, _V]),
+                         _V, _Z, _V, _L, _L, _V]),
+    "mt_conv_layout_bytes": (_Z, [_I, _L, _L]),
+    "mt_conv_layout_prepare": (_I, [_I, _V, _V, _V, _V, _L, _L, _V, _Z, _V]),
     "mt_conv_select_impl": (_I, [_I]),
     "mt_conv_set_debug_buffer": (None, [_V]),
     "mt_conv_bwd_workspace_bytes": (_Z, [C.POINTER(ConvPlanStruct), _I, _L, _L]),

@@ -27,8 +27,10 @@ class ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, sh, emb, handle, graph, avg, num_neigh, *mlp_weights):
         ws = [w.detach() for w in mlp_weights]
+        from .functional import _layout
+
         out = ops.conv_fwd(handle, x.detach(), sh.detach(), emb.detach(), ws, graph.rowptr, graph.perm,
-                           graph.src_sorted, avg, num_neigh)
+                           graph.src_sorted, avg, num_neigh, layout=_layout(graph, sh.detach(), handle))
         ctx.handle, ctx.graph, ctx.avg = handle, graph, avg
         ctx.nw = len(ws)
         ctx.save_for_backward(x, sh, emb, num_neigh if num_neigh is not None else x.new_empty(0), *mlp_weights)

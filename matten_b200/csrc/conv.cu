@@ -17,7 +17,7 @@ MT_DECL(double, 8) MT_DECL(double, 16) MT_DECL(double, 32) MT_DECL(double, 64)
 int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, const void* emb,
                     const void* const* mlp_weights, const int32_t* rowptr, const int32_t* perm,
                     const int32_t* src_sorted, double avg, const void* num_neigh, void* out, void* workspace,
-                    size_t workspace_bytes, int64_t N, int64_t E, cudaStream_t st, int* used);
+                    size_t workspace_bytes, const void* layout, int64_t N, int64_t E, cudaStream_t st, int* used);
 size_t conv_fwd_tc_workspace_bytes(const mt_conv_plan* plan, int64_t N, int64_t E);
 void conv_fwd_tc_set_debug(void* p);
 
@@ -164,7 +164,8 @@ size_t mt_conv_fwd_workspace_bytes(const mt_conv_plan* plan, int dtype, int64_t 
 int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* sh, const void* emb,
                 const void* const* mlp_weights, const int32_t* rowptr, const int32_t* perm,
                 const int32_t* src_sorted, double avg_num_neighbors, const void* num_neigh, void* out,
-                void* workspace, size_t workspace_bytes, int64_t N, int64_t E, mt_stream stream) {
+                void* workspace, size_t workspace_bytes, const void* layout, int64_t N, int64_t E,
+                mt_stream stream) {
   MT_ENTRY_GUARD();
   int rc = validate_plan(plan);
   if (rc != MT_OK) return rc;
@@ -181,7 +182,7 @@ int mt_conv_fwd(const mt_conv_plan* plan, int dtype, const void* x, const void* 
     if (impl != 2) {
       int used = 0;
       rc = conv_fwd_tc_try(plan, x, sh, emb, mlp_weights, rowptr, perm, src_sorted, avg_num_neighbors, num_neigh,
-                           out, workspace, workspace_bytes, N, E, as_stream(stream), &used);
+                           out, workspace, workspace_bytes, layout, N, E, as_stream(stream), &used);
       if (rc != MT_OK) return rc;
       if (used) return MT_OK;
       if (impl == 1)

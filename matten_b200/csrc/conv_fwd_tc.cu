@@ -70,6 +70,79 @@ static TcWorkspace tc_workspace(const mt_conv_plan* plan, int64_t N, int64_t E) 
   return w;
 }
 
+// layer-invariant part kept by the caller (mt_conv_layout_prepare): same regions as in the workspace
+struct TcLayout {
+  size_t rowptr_pad, scan_tmp, orig_pad, src_pad, ypairs, total;
+  int64_t cols_max;
+  size_t scan_bytes;
+};
+static TcLayout tc_layout(int y_lmax, int64_t N, int64_t E) {
+  TcLayout w;
+  w.cols_max = (E + 3 * N + 3) & ~(int64_t)3;
+  if (w.cols_max < 4) w.cols_max = 4;
+  w.scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, w.scan_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)(N + 1));
+  size_t o = 0;
+  w.rowptr_pad = o;
+  o += align256((size_t)(N + 1) * 4 * 2);
+  w.scan_tmp = o;
+  o += align256(w.scan_bytes);
+  w.orig_pad = o;
+  o += align256((size_t)w.cols_max * 4);
+  w.src_pad = o;
+  o += align256((size_t)w.cols_max * 4);
+  w.ypairs = o;
+  o += align256((size_t)(w.cols_max / 2) * 2 * sh_pad_len(y_lmax) * 4);
+  w.total = o;
+  return w;
+}
+
+static int tc_prepare_order(const int32_t* rowptr, const int32_t* perm, const int32_t* src_sorted, int64_t N,
+                            int32_t* degp, int32_t* rowptr_pad, void* scan_tmp, size_t scan_bytes, int32_t* orig_pad,
+                            int32_t* src_pad, cudaStream_t st) {
+  tc_pad_degree_kernel<<<(unsigned)ceil_div<int64_t>(N + 1, 256), 256, 0, st>>>(rowptr, N, degp);
+  MT_LAUNCH_OK();
+  MT_CUDA_OK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, degp, rowptr_pad, (int)(N + 1), st));
+  count_launch();
+  int64_t g = ceil_div<int64_t>(N * 32, 256);
+  if (g > (int64_t)kNumSMs * 32) g = (int64_t)kNumSMs * 32;
+  if (g < 1) g = 1;
+  tc_pad_layout_kernel<<<(unsigned)g, 256, 0, st>>>(rowptr, rowptr_pad, perm, src_sorted, N, orig_pad, src_pad);
+  MT_LAUNCH_OK();
+  return MT_OK;
+}
+
+extern "C" size_t mt_conv_layout_bytes(int y_lmax, int64_t N, int64_t E) {
+  if (y_lmax < 0 || y_lmax > MT_LMAX || N <= 0 || E < 0) return 0;
+  return tc_layout(y_lmax, N, E).total;
+}
+
+extern "C" int mt_conv_layout_prepare(int y_lmax, const void* sh, const int32_t* rowptr, const int32_t* perm,
+                                      const int32_t* src_sorted, int64_t N, int64_t E, void* layout,
+                                      size_t layout_bytes, mt_stream stream) {
+  MT_ENTRY_GUARD();
+  MT_REQUIRE(y_lmax >= 0 && y_lmax <= MT_LMAX && N > 0 && E >= 0, "conv layout: bad arguments");
+  MT_REQUIRE(E + 3 * N < (int64_t)2147483647, "conv layout: too many edges");
+  const TcLayout L = tc_layout(y_lmax, N, E);
+  MT_REQUIRE(layout && layout_bytes >= L.total && (reinterpret_cast<uintptr_t>(layout) & 255) == 0,
+             "conv layout: buffer of mt_conv_layout_bytes() bytes, 256-byte aligned, required");
+  MT_REQUIRE(rowptr && (E == 0 || (sh && perm && src_sorted)), "null pointer");
+  cudaStream_t st = as_stream(stream);
+  const uintptr_t base = reinterpret_cast<uintptr_t>(layout);
+  int32_t* degp = reinterpret_cast<int32_t*>(base + L.rowptr_pad);
+  int32_t* rowptr_pad = degp + (N + 1);
+  int32_t* orig_pad = reinterpret_cast<int32_t*>(base + L.orig_pad);
+  int rc = tc_prepare_order(rowptr, perm, src_sorted, N, degp, rowptr_pad, reinterpret_cast<void*>(base + L.scan_tmp),
+                            L.scan_bytes, orig_pad, reinterpret_cast<int32_t*>(base + L.src_pad), st);
+  if (rc != MT_OK) return rc;
+  int64_t g = ceil_div<int64_t>(L.cols_max, 256);
+  if (g > (int64_t)kNumSMs * 8) g = (int64_t)kNumSMs * 8;
+  tc_ypairs_kernel<<<(unsigned)g, 256, 0, st>>>(static_cast<const float*>(sh), rowptr_pad, orig_pad, N, y_lmax,
+                                                reinterpret_cast<float*>(base + L.ypairs));
+  MT_LAUNCH_OK();
+  return MT_OK;
+}
+
 size_t conv_fwd_tc_workspace_bytes(const mt_conv_plan* plan, int64_t N, int64_t E) {
   if (!tc_plan_qualifies(plan) || N <= 0) return 0;
   return tc_workspace(plan, N, E).total;
@@ -101,7 +174,7 @@ static EncodeTiledFn encode_tiled_fn() {
 int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, const void* emb,
                     const void* const* mlp_weights, const int32_t* rowptr, const int32_t* perm,
                     const int32_t* src_sorted, double avg, const void* num_neigh, void* out, void* workspace,
-                    size_t workspace_bytes, int64_t N, int64_t E, cudaStream_t st, int* used) {
+                    size_t workspace_bytes, const void* layout, int64_t N, int64_t E, cudaStream_t st, int* used) {
   *used = 0;
   if (!tc_plan_qualifies(plan)) return MT_OK;
   if (E + 3 * N >= (int64_t)2147483647 || N >= (int64_t)2147483647) return MT_OK;
@@ -142,19 +215,20 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
     p.hplanes = reinterpret_cast<__nv_bfloat16*>(base + W.hplanes);
     p.ypairs = reinterpret_cast<float*>(base + W.ypairs);
     p.cols_max = W.cols_max;
-    // (1) padded column order
-    tc_pad_degree_kernel<<<(unsigned)ceil_div<int64_t>(N + 1, 256), 256, 0, st>>>(rowptr, N, degp);
-    MT_LAUNCH_OK();
-    size_t scan_bytes = W.scan_bytes;
-    MT_CUDA_OK(cub::DeviceScan::ExclusiveSum(reinterpret_cast<void*>(base + W.scan_tmp), scan_bytes, degp, p.rowptr_pad,
-                                             (int)(N + 1), st));
-    count_launch();
-    {
-      int64_t g = ceil_div<int64_t>(N * 32, 256);
-      if (g > (int64_t)kNumSMs * 32) g = (int64_t)kNumSMs * 32;
-      if (g < 1) g = 1;
-      tc_pad_layout_kernel<<<(unsigned)g, 256, 0, st>>>(rowptr, p.rowptr_pad, perm, src_sorted, N, p.orig_pad, p.src_pad);
-      MT_LAUNCH_OK();
+    if (layout != nullptr) {
+      // prepared once per batch by mt_conv_layout_prepare: padded column order + sh pair rows
+      const TcLayout L = tc_layout(plan->tc_y_lmax, N, E);
+      const uintptr_t lb = reinterpret_cast<uintptr_t>(layout);
+      p.rowptr_pad = reinterpret_cast<int32_t*>(lb + L.rowptr_pad) + (N + 1);
+      p.orig_pad = reinterpret_cast<int32_t*>(lb + L.orig_pad);
+      p.src_pad = reinterpret_cast<int32_t*>(lb + L.src_pad);
+      p.ypairs = reinterpret_cast<float*>(lb + L.ypairs);
+      p.skip_y = 1;
+    } else {
+      // (1) padded column order
+      int rc = tc_prepare_order(rowptr, perm, src_sorted, N, degp, p.rowptr_pad, reinterpret_cast<void*>(base + W.scan_tmp),
+                                W.scan_bytes, p.orig_pad, p.src_pad, st);
+      if (rc != MT_OK) return rc;
     }
     // (2) hidden layers of the radial MLP + sh pair rows, per padded column
     {

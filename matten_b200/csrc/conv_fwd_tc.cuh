@@ -88,6 +88,7 @@ struct ConvTcParams {
   __nv_bfloat16* hplanes;     // [3][4][cols_max][8] bf16: plane, k-group, column, k % 8
   float* ypairs;              // [cols_max / 2][2 * y_pad]: pair-interleaved padded sh rows
   int64_t cols_max;           // allocated columns (E + 3 N rounded up to 4)
+  int skip_y;                 // ypairs come prepared (mt_conv_layout_prepare): the hidden-layer kernel leaves them alone
   float avg;
   const float* num_neigh;
   float* out;
@@ -583,7 +584,7 @@ __global__ void __launch_bounds__(kHidThreads) tc_edge_hidden_kernel(const ConvT
     const int oe = in ? p.orig_pad[c] : 0;
     const bool real = in && oe >= 0;
     const int64_t orig = oe >= 0 ? oe : (-1 - oe);
-    if (in) {
+    if (in && !p.skip_y) {
       // sh components -> pair-interleaved padded row: degree-l block at position sh_pad_pos(l)
       const float* __restrict__ yr = p.sh + orig * yn;
       float* yo = p.ypairs + (c >> 1) * ystride + (c & 1);
@@ -652,6 +653,29 @@ __global__ void __launch_bounds__(kHidThreads) tc_edge_hidden_kernel(const ConvT
   }
 }
 
+// sh rows -> pair-interleaved padded rows, one lane per column (the layer-invariant half of the stage above, run once
+// per batch by mt_conv_layout_prepare)
+__global__ void __launch_bounds__(256) tc_ypairs_kernel(const float* __restrict__ sh, const int32_t* __restrict__ rowptr_pad,
+                                                        const int32_t* __restrict__ orig_pad, int64_t N, int ylmax,
+                                                        float* __restrict__ ypairs) {
+  const int yn = (ylmax + 1) * (ylmax + 1);
+  const int ystride = 2 * sh_pad_len(ylmax);
+  const int64_t cols = rowptr_pad[N];
+  for (int64_t c = blockIdx.x * 256ll + threadIdx.x; c < cols; c += (int64_t)gridDim.x * 256) {
+    const int oe = orig_pad[c];
+    const int64_t orig = oe >= 0 ? oe : (-1 - oe);
+    const float* __restrict__ yr = sh + orig * yn;
+    float* yo = ypairs + (c >> 1) * ystride + (c & 1);
+#pragma unroll
+    for (int l = 0; l <= MT_LMAX; ++l) {
+      if (l <= ylmax) {
+#pragma unroll
+        for (int k = 0; k < 2 * l + 1; ++k) yo[2 * (sh_pad_pos(l) + k)] = yr[l * l + k];
+      }
+    }
+  }
+}
+
 // The same stage for the MLP shape every matten config uses (n_rad <= 8 -> 32 -> 32 -> W, silu): lane == column, all
 // 32 hidden outputs of the column in registers, weights by warp-wide broadcast LDS.128.  Per input channel a lane
 // issues 8 LDS.128 and 16 FFMA2 and nothing else (the generic kernel above spends 40 % of its instructions on
@@ -676,7 +700,7 @@ __global__ void __launch_bounds__(256) tc_edge_hidden_fast_kernel(const ConvTcPa
     const int oe = p.orig_pad[c];
     const bool real = oe >= 0;
     const int64_t orig = real ? oe : (-1 - oe);
-    {  // sh components -> pair-interleaved padded row: degree-l block at position sh_pad_pos(l)
+    if (!p.skip_y) {  // sh components -> pair-interleaved padded row: degree-l block at position sh_pad_pos(l)
       const float* __restrict__ yr = p.sh + orig * yn;
       float* yo = p.ypairs + (c >> 1) * ystride + (c & 1);
 #pragma unroll

@@ -73,6 +73,12 @@ def linear(handle: ops.LinPlanHandle, x, weight, species_perm=None, species_ptr=
     return ops.linear_fwd(handle, x.detach(), weight.detach(), species_perm, species_ptr)
 
 
+def _layout(graph, sh, handle):
+    """The batch's shared tensor-core layout (GraphCache.conv_layout), when the graph object keeps one."""
+    f = getattr(graph, "conv_layout", None)
+    return f(sh, handle.tc_y_lmax) if f is not None else None
+
+
 def conv(handle: ops.ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Tensor], graph,
          avg_num_neighbors: Optional[float], num_neigh=None):
     if _needs_grad(x, *mlp_weights):
@@ -80,7 +86,7 @@ def conv(handle: ops.ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Ten
 
         return A.ConvFn.apply(x, sh, emb, handle, graph, avg_num_neighbors, num_neigh, *mlp_weights)
     return ops.conv_fwd(handle, x.detach(), sh, emb, [w.detach() for w in mlp_weights], graph.rowptr,
-                        graph.perm, graph.src_sorted, avg_num_neighbors, num_neigh)
+                        graph.perm, graph.src_sorted, avg_num_neighbors, num_neigh, layout=_layout(graph, sh, handle))
 
 
 def gate(x, tables, affine_a=None, affine_b=None):

@@ -34,6 +34,7 @@ class GraphCache:
         self._species = None
         self._graph_ptr = None
         self._sender = None
+        self._conv_layout = None
 
     def species_groups(self, species_index: torch.Tensor, num_species: int):
         if self._species is None or self._species[0] != num_species:
@@ -50,6 +51,16 @@ class GraphCache:
             ptr, _ = ops.csr_by_key(batch, num_graphs, False, self.flag)
             self._graph_ptr = ptr
         return self._graph_ptr
+
+    def conv_layout(self, sh: torch.Tensor, y_lmax: Optional[int]):
+        """Layer-invariant inputs of the fp32 tensor-core convolution, built by the first PointConv layer of the
+        forward and reused by the others (all layers see the same graph and the same edge_attrs tensor)."""
+        if sh.dtype != torch.float32 or y_lmax is None or self.E == 0:
+            return None
+        key = (sh.data_ptr(), sh._version, int(y_lmax))
+        if self._conv_layout is None or self._conv_layout[0] != key:
+            self._conv_layout = (key, ops.conv_layout(sh, y_lmax, self.rowptr, self.perm, self.src_sorted, self.N), sh)
+        return self._conv_layout[1]
 
     def sender_csr(self):
         """CSR over senders of the receiver-sorted edge list (for the backward pass)."""

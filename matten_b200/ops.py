@@ -254,9 +254,11 @@ class ConvPlanHandle:
         s.tc_num_parts = 0
         tc = getattr(uvu_plan, "tc", None)
         self.tc_tables = []
+        self.tc_y_lmax = None  # set when the plan has a tensor-core path (its layout can then be shared by layers)
         if tc is not None and tc.parts:
             s.tc_num_parts = len(tc.parts)
             s.tc_y_lmax = tc.y_lmax
+            self.tc_y_lmax = int(tc.y_lmax)
             for i, part in enumerate(tc.parts):
                 tabs = [t.to(device).contiguous() for t in (part.row_wcol, part.bi_hdr, part.bi_lane, part.q_list)]
                 self.tc_tables.append(tabs)
@@ -286,8 +288,26 @@ class ConvPlanHandle:
 
 
 @_on_device
+def conv_layout(sh, y_lmax: int, rowptr, perm, src_sorted, N: int):
+    """The layer-invariant inputs of the fp32 tensor-core convolution (padded column order of the receiver-sorted
+    edge list + pair-interleaved sh rows), prepared once per batch and passed to every ``conv_fwd`` of that batch."""
+    lib = _lib.load()
+    sh = _req(sh, "edge_attrs", torch.float32)
+    E = sh.shape[0]
+    if sh.shape[1] != (y_lmax + 1) ** 2:
+        raise ValueError(f"conv_layout: edge_attrs has {sh.shape[1]} columns, expected {(y_lmax + 1) ** 2}")
+    nbytes = lib.mt_conv_layout_bytes(int(y_lmax), N, E)
+    if nbytes == 0:
+        return None
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=sh.device)  # the caching allocator aligns to 512 bytes
+    check(lib.mt_conv_layout_prepare(int(y_lmax), _p(sh), _p(rowptr), _p(perm), _p(src_sorted), N, E, _p(buf), nbytes,
+                                     _stream(sh)))
+    return buf
+
+
+@_on_device
 def conv_fwd(handle: ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Tensor], rowptr, perm,
-             src_sorted, avg_num_neighbors: Optional[float], num_neigh=None):
+             src_sorted, avg_num_neighbors: Optional[float], num_neigh=None, layout=None):
     lib = _lib.load()
     x = _req(x, "node_features")
     sh = _req(sh, "edge_attrs", x.dtype)
@@ -317,7 +337,8 @@ def conv_fwd(handle: ConvPlanHandle, x, sh, emb, mlp_weights: Sequence[torch.Ten
         ev0.record()
     check(lib.mt_conv_fwd(C.byref(st), _dt(x), _p(x), _p(sh), _p(emb), wptrs, _p(rowptr), _p(perm),
                           _p(src_sorted), float(avg_num_neighbors) if avg_num_neighbors is not None else 0.0,
-                          _p(num_neigh), _p(out), _p(ws), ws_bytes, N, E, _stream(x)))
+                          _p(num_neigh), _p(out), _p(ws), ws_bytes,
+                          _p(layout) if x.dtype == torch.float32 else None, N, E, _stream(x)))
     if CONV_EVENTS is not None:
         ev1.record()
         CONV_EVENTS.append(((pl.x_dim, pl.y_dim, pl.out_dim, pl.weight_numel, N, E), ev0, ev1))
