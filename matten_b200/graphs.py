@@ -21,12 +21,20 @@ class CapturedForward:
         self.model = model
         self.warmup = warmup
         self._graphs: Dict[Tuple, tuple] = {}
+        self._tensors = None
 
     def _model_version(self) -> int:
         """Changes whenever a parameter or buffer is written in place (optimizer step, load_state_dict): derived
         vectors cached outside the graph (BatchNorm.eval_affine) would otherwise go stale inside a capture."""
-        return hash(tuple(t._version for t in self.model.parameters()) +
-                    tuple(t._version for t in self.model.buffers()))
+        ts = self._tensors
+        if ts is None:  # walking the module tree costs ~0.3 ms: do it once (call invalidate() after model.to(...))
+            ts = self._tensors = list(self.model.parameters()) + list(self.model.buffers())
+        return hash(tuple(t._version for t in ts))
+
+    def invalidate(self):
+        """Forget the captures and the cached tensor list (after the model's tensors were replaced, e.g. ``.to``)."""
+        self._tensors = None
+        self._graphs.clear()
 
     def _signature(self, batch, slot: int = 0) -> Tuple:
         return (slot, self._model_version()) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) if isinstance(v, torch.Tensor) else (k, v)
