@@ -333,10 +333,12 @@ __device__ __forceinline__ void lin_stream_block(const T* __restrict__ ws, const
   }
 }
 
+// CTA-synchronous variant (all warps walk the blocks together over a tile of 16 or 32 nodes, NB = 2 / 4 nodes per
+// lane): better for the short rows of lin1 / sc, where amortising the weight loads over more nodes matters most.
 constexpr int kStreamTiles = 8;  // at most: consecutive tiles of one species per CTA (weight slices staged once)
 
 template <typename T>
-__global__ void __launch_bounds__(256) linear_stream_kernel(const LinParams p, const LinStream e) {
+__global__ void __launch_bounds__(256) linear_sync_kernel(const LinParams p, const LinStream e) {
   extern __shared__ __align__(16) unsigned char lin_smem[];
   __shared__ int s_nodes[kStreamTiles * 32];
   T* wsm = reinterpret_cast<T*>(lin_smem);
@@ -481,6 +483,219 @@ __global__ void __launch_bounds__(256) linear_stream_kernel(const LinParams p, c
   }
 }
 
+// Warp-private variant of the same arithmetic: a warp owns NB nodes at a time and walks ALL blocks over them with
+// its own double-buffered rows and its own cp.async groups -- no CTA barrier after the weight slices are in place, so
+// the eight warps drift apart and one warp's copies run under another's FMAs.  (The CTA-synchronous version spent its
+// time at the two barriers per block: 5.5 k of 16 k stall samples on lin2, ncu r2_lin_full.)
+constexpr int kWarpNB = 2;       // nodes per warp and step
+constexpr int kWarpGroupsMax = 4;  // node groups per warp: a CTA covers 8 x kWarpNB x groups nodes of one species
+
+template <typename T, int D, int NB>
+__device__ __forceinline__ void lin_warp_block(const T* __restrict__ ws, const T* __restrict__ xs, int RS, int mi4,
+                                               int mo, int ncount, const int* __restrict__ nodes,
+                                               T* __restrict__ OUT, int out_dim, int out_off, T scale, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  int lpn = 32;  // lanes per channel group: the smallest of 32/16/8/4 covering mul_out (32 when mul_out > 16)
+  while (lpn > 4 && (lpn >> 1) >= mo) lpn >>= 1;
+  const int subs = 32 / lpn, ks = lane / lpn, wl = lane - ks * lpn;
+  const int ustep = 4 * subs;
+  for (int w0 = 0; w0 < mo; w0 += lpn) {
+    const int w = w0 + wl;
+    const bool wok = w < mo;
+    T acc[NB][D];
+    const T* xq[NB];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+      for (int m = 0; m < D; ++m) acc[nb][m] = T(0);
+      xq[nb] = xs + (size_t)nb * RS + ks * 4 * D;  // rows past ncount hold stale finite data; never stored
+    }
+    const T* wq = ws + (wok ? w : 0) + ks * 4 * mo;
+    for (int u = ks * 4; u < mi4; u += ustep) {
+      T wv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wv[k] = wq[k * mo];
+      wq += ustep * mo;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        T xv[4 * D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) lin_ld4<T>(xq[nb] + 4 * i, *reinterpret_cast<T(*)[4]>(&xv[4 * i]));
+        xq[nb] += ustep * D;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int m = 0; m < D; ++m) acc[nb][m] = fma(wv[k], xv[k * D + m], acc[nb][m]);
+      }
+    }
+    for (int off = lpn; off < 32; off <<= 1) {  // sum the k-splits (fixed order: deterministic)
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int m = 0; m < D; ++m) acc[nb][m] += __shfl_xor_sync(0xffffffffu, acc[nb][m], off);
+    }
+    if (wok && ks == 0) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        if (nb < ncount) {
+          T* dst = OUT + (size_t)nodes[nb] * out_dim + out_off + w * D;
+#pragma unroll
+          for (int m = 0; m < D; ++m) dst[m] = accumulate ? (dst[m] + acc[nb][m] * scale) : acc[nb][m] * scale;
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) linear_stream_kernel(const LinParams p, const LinStream e) {
+  extern __shared__ __align__(16) unsigned char lin_smem[];
+  __shared__ int s_nodes[8 * kWarpNB * kWarpGroupsMax];
+  T* wsm = reinterpret_cast<T*>(lin_smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int super = e.tnode;  // 8 warps x kWarpNB x groups
+  // locate (species, tile-in-species)
+  int tile = blockIdx.x, s = 0;
+  int64_t begin = 0, end = 0;
+  if (p.S == 1 && p.sptr == nullptr) {
+    begin = (int64_t)tile * super;
+    end = imin64(begin + super, p.N);
+    if (begin >= p.N) return;
+  } else {
+    bool found = false;
+    for (s = 0; s < p.S; ++s) {
+      const int cnt = p.sptr[s + 1] - p.sptr[s];
+      const int nt = (cnt + super - 1) / super;
+      if (tile < nt) {
+        begin = p.sptr[s] + (int64_t)tile * super;
+        end = imin64(begin + super, (int64_t)p.sptr[s + 1]);
+        found = true;
+        break;
+      }
+      tile -= nt;
+    }
+    if (!found) return;
+  }
+  const int tn_all = (int)(end - begin);
+  for (int i = tid; i < tn_all; i += 256) s_nodes[i] = p.sperm ? p.sperm[begin + i] : (int)(begin + i);
+  const T* __restrict__ X = static_cast<const T*>(p.x);
+  const T* __restrict__ W = static_cast<const T*>(p.weight);
+  T* __restrict__ OUT = static_cast<T*>(p.out);
+  constexpr int V = 16 / (int)sizeof(T);  // elements per 16-byte copy
+  // this species' weight slices, [mi4][mo] per block (rows mi..mi4 zero); asynchronous copies, all in flight at once.
+  // Rows of mo contiguous elements: 16 bytes per copy when mo allows.
+  for (int b = 0; b < p.num_blocks; ++b) {
+    const int mi = p.mul_in[b], mo = p.mul_out[b], mi4 = (mi + 3) & ~3;
+    T* dst = wsm + e.w_smem_off[b];
+    if (!p.transpose && e.w_vec[b]) {
+      const int rowv = mo / V;  // vectors per row
+      const int nvec = mi4 * rowv;
+      int u = tid / rowv, c = tid - u * rowv;          // one division per thread and block; then additive
+      const int du = 256 / rowv, dc = 256 - du * rowv;
+      for (int v = tid; v < nvec; v += 256) {
+        const bool ok = u < mi;
+        const T* src = W + (ok ? (size_t)p.w_off[b] + ((size_t)u * p.S + s) * mo + c * V : 0);
+        const uint32_t da = (uint32_t)__cvta_generic_to_shared(dst + u * mo + c * V);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        u += du; c += dc;
+        if (c >= rowv) { c -= rowv; ++u; }
+      }
+    } else {
+      for (int u = warp; u < mi4; u += 8)
+        for (int w = lane; w < mo; w += 32) {
+          const bool ok = u < mi;
+          const size_t off = !ok ? 0
+                             : p.transpose ? (size_t)p.w_off[b] + ((size_t)w * p.S + s) * mi + u
+                                           : (size_t)p.w_off[b] + ((size_t)u * p.S + s) * mo + w;
+          lin_cp_async<T>(dst + u * mo + w, W + off, ok);
+        }
+    }
+  }
+  lin_cp_commit();
+  lin_cp_wait<0>();
+  __syncthreads();  // weights and s_nodes in place: the only CTA-wide barrier
+
+  // ---- from here on every warp runs on its own
+  const int nb_ = p.num_blocks;
+  const int ngroups = (tn_all + 8 * kWarpNB - 1) / (8 * kWarpNB);
+  // my groups: node offsets (g * 8 + warp) * kWarpNB
+  int mygroups = 0;
+  for (int g = 0; g < ngroups; ++g)
+    if ((g * 8 + warp) * kWarpNB < tn_all) ++mygroups;
+  if (mygroups == 0) return;
+  const int nsteps = mygroups * nb_;
+  T* xw = wsm + ((e.w_total + 3) & ~3) + (size_t)warp * 2 * kWarpNB * e.rs;  // [2][kWarpNB][rs]
+  const uint32_t xw_s = (uint32_t)__cvta_generic_to_shared(xw);
+  auto issue = [&](int step) {
+    const int g = step / nb_, b = step - g * nb_;
+    const int mi = p.mul_in[b], d = p.dim[b];
+    const int seg = mi * d, segp = (((mi + 3) & ~3) * d + 3) & ~3;  // copied + zero-filled up to the padded length
+    const int n0 = (g * 8 + warp) * kWarpNB;
+    const uint32_t buf_s = xw_s + (uint32_t)((step & 1) * kWarpNB * e.rs * (int)sizeof(T));
+    if (mi > 0) {
+#pragma unroll
+      for (int nb = 0; nb < kWarpNB; ++nb) {
+        if (n0 + nb >= tn_all) break;
+        const T* src = X + (size_t)s_nodes[n0 + nb] * p.in_dim + p.in_off[b];
+        const uint32_t drow = buf_s + (uint32_t)(nb * e.rs * (int)sizeof(T));
+        if (e.vec_ok[b]) {
+          for (int q = lane * V; q < segp; q += 32 * V) {
+            const int n = min(V, seg - q);  // elements really there
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(drow + q * (int)sizeof(T)),
+                         "l"(src + (n > 0 ? q : 0)), "r"(n > 0 ? n * (int)sizeof(T) : 0)
+                         : "memory");
+          }
+        } else {
+          T* dst = xw + (size_t)(step & 1) * kWarpNB * e.rs + (size_t)nb * e.rs;
+          for (int q = lane; q < segp; q += 32) lin_cp_async<T>(dst + q, src + (q < seg ? q : 0), q < seg);
+        }
+      }
+    }
+    lin_cp_commit();
+  };
+  // rows of a partial last group are never copied: make them finite once (they are multiplied, never stored)
+  for (int i = lane; i < 2 * kWarpNB * e.rs; i += 32) xw[i] = T(0);
+  __syncwarp();
+  issue(0);
+  for (int step = 0; step < nsteps; ++step) {
+    if (step + 1 < nsteps) {
+      issue(step + 1);
+      lin_cp_wait<1>();
+    } else {
+      lin_cp_wait<0>();
+    }
+    __syncwarp();  // every lane's copies of this step have landed
+    const int g = step / nb_, b = step - g * nb_;
+    const int n0 = (g * 8 + warp) * kWarpNB;
+    const int ncount = min(kWarpNB, tn_all - n0);
+    const int mi = p.mul_in[b], mo = p.mul_out[b], d = p.dim[b];
+    const T* xs = xw + (size_t)(step & 1) * kWarpNB * e.rs;
+    const int* nodes = s_nodes + n0;
+    if (mi == 0) {
+      if (!p.accumulate) {
+        const int span = mo * d;
+        for (int j = 0; j < ncount; ++j)
+          for (int q = lane; q < span; q += 32) OUT[(size_t)nodes[j] * p.out_dim + p.out_off[b] + q] = T(0);
+      }
+    } else {
+      const T* ws = wsm + e.w_smem_off[b];
+      const int mi4 = (mi + 3) & ~3;
+      const T sc = T(p.scale[b]);
+#define MT_LIN_BLOCK(DD) \
+  lin_warp_block<T, DD, kWarpNB>(ws, xs, e.rs, mi4, mo, ncount, nodes, OUT, p.out_dim, p.out_off[b], sc, p.accumulate)
+      switch (d) {
+        case 1: MT_LIN_BLOCK(1); break;
+        case 3: MT_LIN_BLOCK(3); break;
+        case 5: MT_LIN_BLOCK(5); break;
+        case 7: MT_LIN_BLOCK(7); break;
+        default: MT_LIN_BLOCK(9); break;
+      }
+#undef MT_LIN_BLOCK
+    }
+    __syncwarp();  // the buffer is refilled by step + 2
+  }
+}
+
 // =========================================================================
 // Gate (+ folded BatchNorm affine)      reference src/matten/nn/utils.py:134-140,418
 // =========================================================================
@@ -571,20 +786,50 @@ static int linear_fwd_round(int dtype, const mt_lin_block* const* blocks, int nu
       e.w_vec[b] = (k.mul_out % V == 0) && (k.w_off % V == 0) && ((uintptr_t)weight % 16 == 0) && k.mul_out / V <= 256;
     }
     e.rs = rs + 4;
+    if (in_dim < 512) {  // short rows: CTA-synchronous tiles
     int tnode = 32;
-    auto need = [&](int tn) { return ((size_t)((e.w_total + 3) & ~3) + 2 * (size_t)tn * e.rs) * es; };
-    // two resident CTAs per SM (16 warps, one CTA's copies under the other's arithmetic) beat one big tile
-    while (tnode > 8 && need(tnode) > (size_t)(kStreamSmemBytes / 2 - 8 * 1024)) tnode >>= 1;
+      auto need = [&](int tn) { return ((size_t)((e.w_total + 3) & ~3) + 2 * (size_t)tn * e.rs) * es; };
+      // two resident CTAs per SM (16 warps, one CTA's copies under the other's arithmetic) beat one big tile
+      while (tnode > 8 && need(tnode) > (size_t)(kStreamSmemBytes / 2 - 8 * 1024)) tnode >>= 1;
+      if (ok && need(tnode) <= (size_t)kStreamSmemBytes) {
+        e.tnode = tnode;
+        p.in_dim = in_dim; p.out_dim = out_dim; p.S = num_species;
+        p.x = x; p.weight = weight; p.sperm = species_perm; p.sptr = species_ptr;
+        p.accumulate = accumulate; p.out = out; p.N = N;
+        // several tiles per CTA only when that still leaves >= 4 CTAs per SM
+        int tpc = (int)(N / ((int64_t)tnode * 4 * kNumSMs));
+        tpc = tpc < 1 ? 1 : (tpc > kStreamTiles ? kStreamTiles : tpc);
+        e.tiles_per_cta = tpc;
+        const int64_t tiles = ceil_div<int64_t>(N, (int64_t)tnode * tpc) + (species_ptr ? num_species : 0);
+        MT_REQUIRE(tiles < (int64_t)2147483647, "grid too large");
+        const size_t smem = need(tnode);
+        MT_DISPATCH_DTYPE(dtype, {
+          static thread_local bool configured = false;
+          if (!configured) {
+            MT_CUDA_OK(cudaFuncSetAttribute(linear_sync_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kStreamSmemBytes));
+            configured = true;
+          }
+          linear_sync_kernel<T><<<(unsigned)tiles, 256, smem, st>>>(p, e);
+        });
+        MT_LAUNCH_OK();
+        return MT_OK;
+      }
+  
+    }
+    // a CTA covers 8 warps x kWarpNB nodes x groups of one species; more groups amortise the weight staging, fewer
+    // keep the grid above ~4 CTAs per SM
+    int groups = kWarpGroupsMax;
+    while (groups > 1 && N / (8 * kWarpNB * groups) < 4 * kNumSMs) groups >>= 1;
+    const int tnode = 8 * kWarpNB * groups;
+    auto need = [&](int) { return ((size_t)((e.w_total + 3) & ~3) + 8 * 2 * (size_t)kWarpNB * e.rs) * es; };
     if (ok && need(tnode) <= (size_t)kStreamSmemBytes) {
       e.tnode = tnode;
       p.in_dim = in_dim; p.out_dim = out_dim; p.S = num_species;
       p.x = x; p.weight = weight; p.sperm = species_perm; p.sptr = species_ptr;
       p.accumulate = accumulate; p.out = out; p.N = N;
-      // several tiles per CTA only when that still leaves >= 4 CTAs per SM
-      int tpc = (int)(N / ((int64_t)tnode * 4 * kNumSMs));
-      tpc = tpc < 1 ? 1 : (tpc > kStreamTiles ? kStreamTiles : tpc);
-      e.tiles_per_cta = tpc;
-      const int64_t tiles = ceil_div<int64_t>(N, (int64_t)tnode * tpc) + (species_ptr ? num_species : 0);
+      e.tiles_per_cta = 1;
+      const int64_t tiles = ceil_div<int64_t>(N, (int64_t)tnode) + (species_ptr ? num_species : 0);
       MT_REQUIRE(tiles < (int64_t)2147483647, "grid too large");
       const size_t smem = need(tnode);
       MT_DISPATCH_DTYPE(dtype, {
