@@ -49,7 +49,34 @@ class TensorDataset:
             self.targets.append(t)
             if atom_selector:
                 self.selectors.append(torch.as_tensor(np.asarray(cols[atom_selector][k], dtype=bool)))
+        self.failed_entries: List[Any] = []
+        self._drop_edgeless(keys, dev)
         self.species = sorted({z for s in self.structures for z in s["Z"]})
+
+    def _drop_edgeless(self, keys, dev, chunk: int = 256):
+        """The reference skips crystals without any edge inside ``r_cut`` ("After eliminating self edges, no edges
+        remain", dataset/structure_scalar_tensor.py:357-362) and records them; kept, they would divide by zero
+        neighbours downstream."""
+        from .data.neighbors import batch_from_structures
+        from .predict import _edge_counts
+
+        keep: List[int] = []
+        for i in range(0, len(self.structures), chunk):
+            b = batch_from_structures(self.structures[i:i + chunk], self.r_cut, dev, torch.float64)
+            for j, c in enumerate(_edge_counts(b)):
+                if c > 0:
+                    keep.append(i + j)
+                else:
+                    self.failed_entries.append(keys[i + j])
+        if self.failed_entries:
+            import warnings
+
+            warnings.warn(f"Skipped {len(self.failed_entries)} structures without any edge inside r_cut: "
+                          f"{self.failed_entries[:10]}")
+            self.structures = [self.structures[i] for i in keep]
+            self.targets = [self.targets[i] for i in keep]
+            if self.selectors is not None:
+                self.selectors = [self.selectors[i] for i in keep]
 
     def __len__(self):
         return len(self.structures)
@@ -67,16 +94,19 @@ class TensorDataset:
         return tot / max(n, 1)
 
     def batches(self, batch_size: int, device="cuda", dtype=torch.float32, shuffle: bool = False, seed: int = 0,
-                rank: int = 0, world: int = 1):
+                rank: int = 0, world: int = 1, even: bool = True):
         """Yields (graph batch, target [*, dim], atom selector | None).  Under data parallelism every rank takes
-        every ``world``-th batch (same batch count per rank: the gradient all-reduce needs matching steps)."""
+        every ``world``-th batch.  ``even=True`` (training) drops the last chunks so that every rank runs the same
+        number of steps (the gradient all-reduce needs matching steps); evaluation passes ``even=False`` and sees
+        every crystal (its single all-reduce at the end tolerates uneven counts)."""
         from .data.neighbors import batch_from_structures
 
         order = np.arange(len(self))
         if shuffle:
             np.random.default_rng(seed).shuffle(order)
         chunks = [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
-        chunks = chunks[: len(chunks) // world * world] if world > 1 else chunks
+        if world > 1 and even:
+            chunks = chunks[: len(chunks) // world * world]
         for c in chunks[rank::world]:
             batch = batch_from_structures([self.structures[i] for i in c], self.r_cut, device, dtype)
             target = torch.cat([self.targets[i] for i in c], 0).to(dtype)

@@ -90,14 +90,24 @@ class _TensorModelBase(torch.nn.Module):
         ``tensor_property_to_dict`` output being consumed once per forward."""
         return dict(data)
 
-    def forward(self, data: Dict[str, Tensor], check: bool = True) -> Dict[str, Tensor]:
+    def forward(self, data: Dict[str, Tensor], check: bool = True, mode: Optional[str] = None,
+                task_name: Optional[str] = None, return_labels: bool = False):
         """reference BaseModel.forward (src/matten/model/model.py:143-184): decode (+ identity
-        target transform; the shipped configs use no normaliser)."""
+        target transform; the shipped configs use no normaliser).  ``mode="backbone"`` returns the backbone's graph
+        dict, as in the reference.  DEVIATION: the reference takes a PyG ``DataPoint`` batch and returns the tuple
+        ``(preds, labels)``; here the input is the batched graph dict and the default return is the ``preds`` dict
+        alone -- pass ``return_labels=True`` for the reference's tuple (labels = ``data["y"]`` when present)."""
+        if task_name is not None:
+            self.task_name = task_name
         d = self.preprocess(data)
-        preds = self.decode(d)
+        if mode is not None and str(mode).lower() not in ("none", "backbone"):
+            raise ValueError(f"Expect mode to be one of (None, 'backbone'); got {mode}")
+        preds = self.backbone(d) if mode == "backbone" else self.decode(d)
         self._last_graph = d.get(K.GRAPH_CACHE)  # index bookkeeping + device error word of this forward
         if check and K.GRAPH_CACHE in d:
             d[K.GRAPH_CACHE].raise_if_invalid()
+        if return_labels:
+            return preds, data.get("y", {})
         return preds
 
 

@@ -57,13 +57,15 @@ def main():
               "output_formula": "ijkl=jikl=klij", "reduce": "mean"}
         cls, key = ScalarTensorModel, "elastic_tensor_full"
     hp["average_num_neighbors"] = ds.average_num_neighbors(dev)  # "auto" of the reference
-    torch.manual_seed(3)
-    model = cls(hp, {"allowed_species": ds.species}, task_name=key).to(dev)
-    trainer = Trainer(model, lr=args.lr, weight_decay=args.weight_decay, output_key=key)
     val = None
     if args.val:
         kw = dict(atom_selector="atom_selector") if args.atomic else {}
         val = TensorDataset(args.val, 5.0, key, "irreps", hp["output_formula"], device=dev, **kw)
+    # species of every split (the reference takes them from the whole dataset's statistics)
+    species = sorted(set(ds.species) | (set(val.species) if val is not None else set()))
+    torch.manual_seed(3)
+    model = cls(hp, {"allowed_species": species}, task_name=key).to(dev)
+    trainer = Trainer(model, lr=args.lr, weight_decay=args.weight_decay, output_key=key)
     sched = ReduceLROnPlateau(trainer.opt, mode="min", factor=0.5, patience=50)  # config_final.yaml:17-23
     stopper = EarlyStopping(mode="min", patience=150)                            # materials_tensor.yaml:86-92
     for epoch in range(args.epochs):
@@ -74,7 +76,7 @@ def main():
             n += 1
         msg = f"epoch {epoch}: mean training loss {tot / max(n, 1):.6f} over {n} steps"
         if val is not None:
-            m = trainer.evaluate(val.batches(args.batch_size, dev, rank=rank, world=world))
+            m = trainer.evaluate(val.batches(args.batch_size, dev, rank=rank, world=world, even=False))
             sched.step(m["mae"])
             msg += f", val MAE {m['mae']:.6f}, lr {trainer.opt.lr:g}"
             if stopper.step(m["mae"]):

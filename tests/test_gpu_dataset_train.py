@@ -66,3 +66,33 @@ def test_atomic_nmr_dataset_with_selector_trains():
             assert int(sel.sum()) == target.shape[0]
             losses.append(float(tr.step(batch, target / scale, atom_selector=sel)))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_edgeless_crystals_are_skipped_and_evaluation_sees_every_batch(tmp_path):
+    """Reference behaviour (dataset/structure_scalar_tensor.py:357-362): a crystal without any edge inside r_cut is
+    skipped and recorded; evaluation batches are not truncated to a multiple of the world size."""
+    from matten_b200.dataset import TensorDataset
+
+    dev = torch.device("cuda:0")
+    raw = json.load(open(os.path.join(GOLDEN, "elasticity_n6_reference_format.json")))
+    keys = list(raw["structure"].keys())
+    lonely = json.loads(json.dumps(raw["structure"][keys[0]]))
+    # one atom in a 30 A cubic box: no neighbour within 5 A, not even a periodic image
+    lonely["lattice"]["matrix"] = [[30.0, 0, 0], [0, 30.0, 0], [0, 0, 30.0]]
+    for k in ("a", "b", "c"):
+        if k in lonely["lattice"]:
+            lonely["lattice"][k] = 30.0
+    lonely["sites"] = lonely["sites"][:1]
+    lonely["sites"][0]["abc"] = [0.0, 0.0, 0.0]
+    lonely["sites"][0]["xyz"] = [0.0, 0.0, 0.0]
+    raw["structure"]["lonely"] = lonely
+    raw["elastic_tensor_full"]["lonely"] = raw["elastic_tensor_full"][keys[0]]
+    path = tmp_path / "with_lonely.json"
+    path.write_text(json.dumps(raw))
+    with pytest.warns(UserWarning, match="Skipped 1 structures"):
+        ds = TensorDataset(str(path), 5.0, "elastic_tensor_full", "irreps", "ijkl=jikl=klij", device=dev)
+    assert len(ds) == 6 and ds.failed_entries == ["lonely"] and len(ds.targets) == 6
+    # 6 crystals in batches of 2 = 3 chunks over 2 ranks: training drops the odd chunk, evaluation keeps it
+    n_train = [len(list(ds.batches(2, dev, rank=r, world=2))) for r in (0, 1)]
+    n_eval = [len(list(ds.batches(2, dev, rank=r, world=2, even=False))) for r in (0, 1)]
+    assert n_train == [1, 1] and n_eval == [2, 1]
