@@ -456,8 +456,10 @@ def run_ours(args):
                  "value": pts[0]["value"], "unit": "crystals/s", "ms_per_step": pts[0]["ms_per_step"], "points": pts}
 
     # ---------------- BASELINE config 1: predict() on the 100 example crystals ----------------
+    # single-GPU runs only: predict() shards over the ranks of an initialised process group, so calling it on rank 0
+    # alone would leave the other ranks out of its collectives
     config1 = None
-    if rank == 0 and not args.no_predict:
+    if world == 1 and not args.no_predict:
         config1 = predict_config1(dev)
 
     # ---------------- roofline of the dominant kernel (fused conv) ----------------

@@ -356,6 +356,21 @@ __device__ __forceinline__ void tc_load_xy(const TcUnit u, int col, f2* __restri
   }
 }
 
+// the same loads through running pointers (mode L walks consecutive pairs: additive addressing only)
+template <class B>
+__device__ __forceinline__ void tc_load_xy_ptr(const float* __restrict__ xr, int xstride, const float* __restrict__ yp,
+                                               f2* __restrict__ x2, f2* __restrict__ y2) {
+#pragma unroll
+  for (int m = 0; m < B::D1; ++m) x2[m] = f2(xr[m], xr[xstride + m]);
+  const float4* yr = reinterpret_cast<const float4*>(yp);
+#pragma unroll
+  for (int i = 0; i < B::Y_CNT / 2; ++i) {
+    const float4 v = yr[i];
+    y2[2 * i] = f2(v.x, v.y);
+    y2[2 * i + 1] = f2(v.z, v.w);
+  }
+}
+
 // Both unit loops are kept SMALL on purpose (one edge pair per iteration, no per-path branches when every path of the
 // bundle exists): five warps per scheduler run five different instruction streams, and a loop body that does not stay
 // in the instruction cache stalls on every 128-byte line (ncu: `no_instruction` was the top stall of the unrolled form).
@@ -397,16 +412,23 @@ __device__ __forceinline__ void tc_unit_L(const TcUnit u) {
 #pragma unroll
     for (int p = 1; p < B::NP; ++p) tmem_ld_touch2(wc[p]);
   }
+  const float* xr = u.xs + (size_t)u.cb * u.xstride + u.lt.x;                       // += 2 rows per pair
+  const float* yp = u.ys + (size_t)(u.cb >> 1) * u.ystride + 2 * B::Y_LO;           // += 1 pair row per pair
+  const int xstep = 2 * u.xstride;
+  uint32_t tnext = 2u;
 #pragma unroll 1
   for (int g = 0; g < npairs; ++g) {
     const bool more = g + 1 < npairs;
     if (more) {
 #pragma unroll
       for (int p = 0; p < B::NP; ++p)
-        if ((mask >> p) & 1u) tmem_ld_x2(ta[p] + (uint32_t)(2 * g + 2), wn[p]);  // prefetch the next pair's weights
+        if ((mask >> p) & 1u) tmem_ld_x2(ta[p] + tnext, wn[p]);  // prefetch the next pair's weights
+      tnext += 2u;
     }
     f2 x2[B::D1], y2[B::Y_CNT], w2[B::NP];
-    tc_load_xy<B>(u, u.cb + 2 * g, x2, y2);
+    tc_load_xy_ptr<B>(xr, u.xstride, yp, x2, y2);
+    xr += xstep;
+    yp += u.ystride;
 #pragma unroll
     for (int p = 0; p < B::NP; ++p) w2[p] = f2(__uint_as_float(wc[p].a), __uint_as_float(wc[p].b));
     B::template edge<f2>(x2, y2, w2, acc, mask);
