@@ -288,6 +288,16 @@ int conv_fwd_tc_try(const mt_conv_plan* plan, const void* x, const void* sh, con
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(MT_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    // the h planes [3 planes x 4 k-groups][cols_max][16 bytes] as a 3D byte tensor, box {16, NE, 12}: a chunk's twelve
+    // plane segments in one TMA instruction, landing as the dense [12][NE][16 B] B operand
+    cuuint64_t hdims[3] = {16, (cuuint64_t)p.cols_max, 12};
+    cuuint64_t hstrides[2] = {16, (cuuint64_t)p.cols_max * 16};
+    cuuint32_t hbox[3] = {16, (cuuint32_t)q.ne, 12};
+    cuuint32_t hestr[3] = {1, 1, 1};
+    const CUresult rh = encode(&maps.h[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, p.hplanes, hdims, hstrides, hbox, hestr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rh != CUDA_SUCCESS) return set_error(MT_ECUDA, "cuTensorMapEncodeTiled (h planes) failed (%d)", (int)rh);
   }
   grid = assigned;
   static thread_local size_t configured[2] = {0, 0};

@@ -44,7 +44,7 @@
 namespace mt {
 
 constexpr int kTcK = 32;              // padded size of the last hidden layer == MMA K total
-constexpr int kTcProducerWarps = 3;   // warp 0: chunks + plane / sh copies, warp 1: MMA issue, warp 2: TMA gathers
+constexpr int kTcProducerWarps = 4;   // warp 0: chunks + plane / sh copies, warp 1: MMA issue, warps 2 and 3: TMA gathers (even / odd groups)
 constexpr int kTcConsumerWarps = 16;  // a multiple of 4: warp w reads TMEM quarter w % 4
 constexpr int kTcThreads = 32 * (kTcProducerWarps + kTcConsumerWarps);
 constexpr int kTcMaxTiles = 4;        // M tiles of 128 rows per part
@@ -100,6 +100,7 @@ struct ConvTcParams {
 
 struct alignas(64) TcMaps {
   CUtensorMap m[kTcMaxParts];  // x as a 2D tensor [N][x_dim], box {x_cols, 1}: one per part (its column window)
+  CUtensorMap h[kTcMaxParts];  // h planes as a 3D tensor [12][cols_max][16 bytes], box {16, NE, 12}: one per part (its NE)
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -207,6 +208,16 @@ __device__ __forceinline__ void tma_gather4(void* dst_smem, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::1 "
       "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(smem_u32(dst_smem)),
       "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// TMA tile load of a 3D box (the 12 h-plane segments of a chunk in ONE instruction; out-of-range columns are zero
+// filled and still counted in the transaction bytes)
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
 
@@ -989,17 +1000,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid
                                     // cycles: 16 gathers + 13 bulk copies on one warp were the critical path)
           if (b_uses > 0) mbar_wait(&bar_bfree, (b_uses - 1) & 1, 21);  // previous MMAs have consumed the h planes
           s_mma_b = b;
-          mbar_arrive_expect_tx(&bar_bready, (uint32_t)ncols * 16u * 12u);
+          mbar_arrive_expect_tx(&bar_bready, (uint32_t)NE * 16u * 12u);  // the whole box, whatever ncols is
         }
         __syncwarp();
         MT_TACC(2);
         // the chunk is ONE contiguous range of padded columns: 12 plane segments, the sh pair rows, and one TMA gather
         // of 4 sender rows per 4 columns
-        if (lane < 12) {
-          const int pl = lane >> 2, g = lane & 3;
-          bulk_g2s(sB + (size_t)pl * L.b_plane + (size_t)g * NE * 16,
-                   reinterpret_cast<const unsigned char*>(p.hplanes) + ((size_t)(pl * 4 + g) * p.cols_max + pc0) * 16,
-                   (uint32_t)ncols * 16u, &bar_bready);
+        // (twelve separate bulk copies cost ~3 k issue cycles per chunk on this warp: each TMA instruction is ~250)
+        if (lane == 0) {
+          tma_load_3d(sB, &maps.h[part_id], 0, pc0, 0, &bar_bready);
         } else if (lane == 12) {
           bulk_g2s(smem + L.y_off + (size_t)b * L.y_buf, p.ypairs + (size_t)(pc0 >> 1) * ystride,
                    (uint32_t)(ncols >> 1) * ypair_bytes, &bar_full[b]);
@@ -1022,6 +1031,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid
     MT_TC_TIMER_FLUSH();
   } else if (warp == 1) {
     // ================================================================ MMA issuer
+    // (two issuing warps, even / odd tiles, were measured: 2-4 % slower -- the MMAs are not what a chunk waits for)
     const uint32_t idesc = make_idesc_bf16(128, NE);
     const uint32_t a_lbo = (uint32_t)a_rows * 16, b_lbo = (uint32_t)NE * 16;
     const uint32_t a_plane32 = (uint32_t)L.a_plane, b_plane32 = (uint32_t)L.b_plane;
@@ -1067,8 +1077,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid
       MT_TACC(1);
     }
     MT_TC_TIMER_FLUSH();
-  } else if (warp == 2) {
-    // ================================================================ TMA gathers of the sender rows
+  } else if (warp == 2 || warp == 3) {
+    // ================================================================ TMA gathers of the sender rows (a gather4 costs
+    // its issuing warp ~250 cycles per active lane).  One-tile parts have 256-column chunks = 64 gathers: warps 2 and 3
+    // take the even / odd groups of 4 columns (-5 %); with more tiles (<= 32 gathers per chunk) a second active
+    // producer warp only takes issue slots from the consumers (+3-5 %), so warp 3 idles there.
+    const int ngw = MT == 1 ? 2 : 1;
+    const int gw = warp == 2 ? 0 : 1;
+    if (gw < ngw) {
     const CUtensorMap* map = &maps.m[part_id];
     const uint32_t xrow_bytes = (uint32_t)P.x_cols * 4;
     MT_TC_TIMER();  // 0: wait go, 1: issue
@@ -1081,13 +1097,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const __grid
       const int nn = M.nnodes, ncols = M.ncols, pc0 = M.pc0;
       if (nn < 0) break;
       unsigned char* xs = smem + L.x_off + (size_t)b * L.x_buf;
-      for (int g = lane; g < (ncols >> 2); g += 32) {
+      for (int g = ngw * lane + gw; g < (ncols >> 2); g += 32 * ngw) {
         const int4 r = *reinterpret_cast<const int4*>(p.src_pad + pc0 + 4 * g);
         tma_gather4(xs + (size_t)(4 * g) * xrow_bytes, map, P.x_lo, r.x, r.y, r.z, r.w, &bar_full[b]);
       }
       MT_TACC(1);
     }
     MT_TC_TIMER_FLUSH();
+    }
   } else {
     // ================================================================ consumers
     const int q = warp & 3;
