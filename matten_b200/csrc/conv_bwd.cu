@@ -128,10 +128,11 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
     const size_t fixed = (size_t)p.num_paths * 16;
     // resident CTAs per SM the register budget allows (launch bounds of conv_bwd_kernel) -> shared-memory budget per CTA:
     // the kernel alternates staging / GEMM / contraction phases between barriers, so more small CTAs hide more of it
-    const char* env_t = getenv("MT_BWD_THREADS");
-    const char* env_c = getenv("MT_BWD_CTAS");
-    const int threads1 = (env_t && *env_t) ? atoi(env_t) : 128;  // more, smaller CTAs hide the phase barriers better (r1 sweep)
-    const int per_sm_regs = (env_c && *env_c) ? atoi(env_c) : ((sizeof(T) == 4 ? 3 : 2) * (256 / threads1));
+    // tuning overrides are read from the environment ONCE per process: nothing on the call path touches getenv
+    static const int env_threads = [] { const char* e = getenv("MT_BWD_THREADS"); return (e && *e) ? atoi(e) : 0; }();
+    static const int env_ctas = [] { const char* e = getenv("MT_BWD_CTAS"); return (e && *e) ? atoi(e) : 0; }();
+    const int threads1 = env_threads > 0 ? env_threads : 128;  // more, smaller CTAs hide the phase barriers better (r1 sweep)
+    const int per_sm_regs = env_ctas > 0 ? env_ctas : ((sizeof(T) == 4 ? 3 : 2) * (256 / threads1));
     const size_t budget = (size_t)(227 * 1024) / per_sm_regs - 1024;
     int EC = 32, TN = 1;
     size_t smem = 0;

@@ -147,6 +147,10 @@ def test_species_embed_and_kat(dev):
     ("22x0o+56x0e+100x1o+68x1e+78x2o+112x2e+110x3o+78x3e+90x4e",
      "32x0o+78x0e+16x1o+16x1e+4x2o+4x2e+2x3o+2x3e+2x4e", 3),
     ("32x0e+16x1o", "32x0e+16x1o", 1),
+    # unaligned everything (odd row length, multiplicities not multiples of 4: the 4-byte staging paths, zero-padded
+    # input channels), short rows (CTA-synchronous kernel) and long rows (warp-private kernel)
+    ("5x0e+3x1o+1x2e", "7x0e+3x1o+2x2e", 4),
+    ("131x0e+77x1o+45x2e+3x3o", "9x0e+5x1o+3x2e+1x3o", 5),
 ])
 def test_species_linear_vs_fctp(dev, dtype, irr_in, irr_out, S):
     from matten_b200 import ops
@@ -174,6 +178,11 @@ def test_species_linear_vs_fctp(dev, dtype, irr_in, irr_out, S):
         res = torch.randn(N, lin.irreps_out.dim, dtype=dtype)
         got2 = lin(x.to(dev), perm, ptr, residual=res.to(dev).clone())
         assert rel_err(got2, want + res) < tol(dtype)
+        # a handful of nodes (partial tiles, idle warps) and a single node
+        for n_small in (5, 1):
+            ptr_s, perm_s = ops.csr_by_key(sp[:n_small].to(dev), S, True, flag)
+            got3 = lin(x[:n_small].to(dev), perm_s, ptr_s)
+            assert rel_err(got3, want[:n_small]) < tol(dtype)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
