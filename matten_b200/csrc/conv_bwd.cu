@@ -53,7 +53,11 @@ static BwdLayout bwd_layout(const mt_conv_plan* plan, size_t es, int64_t E) {
   L.partl_off = o;
   o += align256((size_t)L.grid2 * H * Wn * es);
   L.parth_off = o;
-  o += align256((size_t)L.grid3 * (hid > 0 ? hid : 1) * es);
+  {  // one partial per CTA of the generic K3, one per warp of the fast K3
+    const size_t rows = (size_t)L.grid3 > (size_t)kHidFastCtas * kHidFastWarps ? (size_t)L.grid3
+                                                                               : (size_t)kHidFastCtas * kHidFastWarps;
+    o += align256(rows * (hid > 0 ? hid : 1) * es);
+  }
   L.total = o;
   return L;
 }
@@ -109,8 +113,16 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
   p.rs = L.rs;
   p.hid_eb = L.hid_eb;
 
+  // the MLP shape of the matten configs in fp32 takes the lane-per-edge kernels
+  const bool fast_mlp = sizeof(T) == 4 && nl == 3 && p.sizes[0] <= 8 && p.sizes[1] == 32 && p.sizes[2] == 32 &&
+                        p.act == MT_ACT_SILU;
   // K0: hidden pre-activations
-  if (nl > 1) {
+  if (fast_mlp) {
+    int64_t g0 = ceil_div<int64_t>(E, 256);
+    if (g0 > (int64_t)kNumSMs * 8) g0 = (int64_t)kNumSMs * 8;
+    edge_hidden_fast_kernel<<<(unsigned)g0, 256, 0, st>>>(p);
+    MT_LAUNCH_OK();
+  } else if (nl > 1) {
     const size_t smem0 = ((size_t)p.hid_eb * p.rs + (size_t)p.rs * p.rs) * sizeof(T);
     static thread_local size_t cfg0 = 0;
     if (smem0 > cfg0) {
@@ -186,7 +198,22 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
           static_cast<const T*>(p.PARTL), cnt, p.grid2, 0, cnt, T(1) / sqrt(T(H)), static_cast<T*>(grad_w[nl - 1]));
       MT_LAUNCH_OK();
     }
-    if (nl > 1) {
+    if (fast_mlp) {
+      int64_t gf = ceil_div<int64_t>(ceil_div<int64_t>(E, 32), kHidFastWarps);
+      if (gf > kHidFastCtas) gf = kHidFastCtas;
+      mlp_bwd_hidden_fast_kernel<<<(unsigned)gf, 32 * kHidFastWarps, 0, st>>>(p);
+      MT_LAUNCH_OK();
+      const int nparts = (int)gf * kHidFastWarps;
+      int64_t off = 0;
+      for (int l = 0; l + 1 < nl; ++l) {
+        const int64_t cnt = (int64_t)p.sizes[l] * p.sizes[l + 1];
+        reduce_partials_kernel<T><<<(unsigned)ceil_div<int64_t>(cnt, 256), 256, 0, st>>>(
+            static_cast<const T*>(p.PARTH), p.hid_numel, nparts, off, cnt, T(1) / sqrt(T(p.sizes[l])),
+            static_cast<T*>(grad_w[l]));
+        MT_LAUNCH_OK();
+        off += cnt;
+      }
+    } else if (nl > 1) {
       const size_t smem3 = ((size_t)3 * p.hid_eb * p.rs + (size_t)p.rs * p.rs + p.hid_numel) * sizeof(T);
       MT_REQUIRE(smem3 <= 227 * 1024, "hidden MLP too large for the backward kernel");
       static thread_local size_t cfg3 = 0;

@@ -470,6 +470,194 @@ __global__ void __launch_bounds__(256) mlp_bwd_hidden_kernel(const ConvBwdParams
   for (int t = tid; t < p.hid_numel; t += blockDim.x) part[t] = accW[t];
 }
 
+// ---------------------------------------------------------------------------------------------- K0 / K3, fast forms
+// The MLP shape of every matten config (n_rad <= 8 -> 32 -> 32 -> W, silu), fp32: lane == edge, a layer's 32 values in
+// registers, weights by warp-wide broadcast LDS.128 (the generic kernels above walk [edge][k] tiles in shared memory
+// with an integer division per element: 0.5 ms (K0) and 1.0 ms (K3) per layer at 9e5 edges against ~0.1 ms here).
+__device__ __forceinline__ float bwd_sigmoid(float v) {  // ex2.approx + rcp.approx: ~3e-7 relative
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * v));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+
+// y[0..31] += h * W[k][0..31] for a row of a [.][32] matrix in shared memory (broadcast LDS.128)
+__device__ __forceinline__ void bwd_row_fma(float h, const float* __restrict__ wrow, float2 (&acc)[16]) {
+  const float4* wr = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 w = wr[j];
+    fma_pair(h, w.x, w.y, acc[2 * j]);
+    fma_pair(h, w.z, w.w, acc[2 * j + 1]);
+  }
+}
+
+__global__ void __launch_bounds__(256) edge_hidden_fast_kernel(const ConvBwdParams p) {
+  __shared__ __align__(16) float sW0[8 * 32];
+  __shared__ __align__(16) float sW1[32 * 32];
+  const int in0 = p.sizes[0];
+  {
+    const float s0 = rsqrtf((float)in0), s1 = rsqrtf(32.f);
+    const float* w0 = static_cast<const float*>(p.w[0]);
+    const float* w1 = static_cast<const float*>(p.w[1]);
+    for (int t = threadIdx.x; t < 8 * 32; t += 256) sW0[t] = (t >> 5) < in0 ? w0[t] * s0 : 0.f;
+    for (int t = threadIdx.x; t < 32 * 32; t += 256) sW1[t] = w1[t] * s1;
+  }
+  __syncthreads();
+  const float cst = (float)p.act_cst;
+  const float* __restrict__ emb = static_cast<const float*>(p.emb);
+  float4* Z0 = static_cast<float4*>(p.z[0]);
+  float4* Z1 = static_cast<float4*>(p.z[1]);
+  for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < p.E; e += (int64_t)gridDim.x * 256) {
+    const float* er = emb + (size_t)p.perm[e] * in0;
+    float2 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float h = k < in0 ? er[k] : 0.f;
+      bwd_row_fma(h, sW0 + k * 32, acc);
+    }
+    float a1[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      Z0[(size_t)e * 8 + i] = make_float4(acc[2 * i].x, acc[2 * i].y, acc[2 * i + 1].x, acc[2 * i + 1].y);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      a1[2 * i] = acc[i].x * bwd_sigmoid(acc[i].x) * cst;
+      a1[2 * i + 1] = acc[i].y * bwd_sigmoid(acc[i].y) * cst;
+      acc[i] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) bwd_row_fma(a1[k], sW1 + k * 32, acc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      Z1[(size_t)e * 8 + i] = make_float4(acc[2 * i].x, acc[2 * i].y, acc[2 * i + 1].x, acc[2 * i + 1].y);
+  }
+}
+
+// K3: one warp walks chunks of 32 edges (lane == edge).  Per chunk: da2 = sum of the K2 column-group partials,
+// dz1 = da2 silu'(z1) cst, da1 = W1 dz1 / sqrt(32) (W1^T rows by broadcast LDS.128), dz0 = da1 silu'(z0) cst; then the
+// chunk's a1 / dz1 and emb / dz0 go through warp-private shared-memory tiles and every lane accumulates one row of
+// dW1 (lane == input index i: 32 sums in registers) and one column of dW0 (lane == output index j: 8 sums) over ALL
+// its chunks.  One partial [hid_numel] per warp, summed in fixed order by reduce_partials_kernel.
+constexpr int kHidFastWarps = 3;   // 3 x 13.6 KB of tiles + W1^T stay under the 48 KB static limit; 5 CTAs per SM
+constexpr int kHidFastCtas = 5 * kNumSMs;
+struct HidFastTile {
+  float a1[32 * 33];   // [edge][i], stride 33: lane e writes row e, lane i reads column i -- both conflict free
+  float dz0[32 * 33];  // [edge][j]
+  float dz1[32 * 32];  // [edge][j] dense, float4 chunks XOR-swizzled by (edge & 7): broadcast LDS.128 reads
+  float emb[32 * 8];   // [edge][k]
+};
+
+__global__ void __launch_bounds__(32 * kHidFastWarps) mlp_bwd_hidden_fast_kernel(const ConvBwdParams p) {
+  __shared__ __align__(16) float sW1T[32 * 32];  // [j][i] = W1[i][j] / sqrt(32)
+  __shared__ __align__(16) HidFastTile tiles[kHidFastWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int in0 = p.sizes[0];
+  {
+    const float s1 = rsqrtf(32.f);
+    const float* w1 = static_cast<const float*>(p.w[1]);
+    for (int t = tid; t < 32 * 32; t += 32 * kHidFastWarps) sW1T[(t & 31) * 32 + (t >> 5)] = w1[t] * s1;
+  }
+  __syncthreads();
+  HidFastTile& T = tiles[warp];
+  const float cst = (float)p.act_cst;
+  const float* __restrict__ emb = static_cast<const float*>(p.emb);
+  const float4* Z0 = static_cast<const float4*>(p.z[0]);
+  const float4* Z1 = static_cast<const float4*>(p.z[1]);
+  const float4* DHP = static_cast<const float4*>(p.DHP);
+  float2 gw1[16];  // dW1[lane][0..31]
+  float2 gw0[4];   // dW0[0..7][lane]
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gw1[i] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) gw0[i] = make_float2(0.f, 0.f);
+  const int64_t nchunks = (p.E + 31) >> 5;
+  const int64_t wglobal = (int64_t)blockIdx.x * kHidFastWarps + warp, wtotal = (int64_t)gridDim.x * kHidFastWarps;
+  for (int64_t ch = wglobal; ch < nchunks; ch += wtotal) {
+    const int64_t e = ch * 32 + lane;
+    const bool in = e < p.E;
+    const int64_t es = in ? e : p.E - 1;  // lanes past the end compute on the last edge and contribute zeros
+    // da2, dz1
+    float dz1[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int cg = 0; cg < p.ncg; ++cg) {
+        const float4 v = DHP[((size_t)cg * p.E + es) * 8 + i];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      const float4 z = Z1[(size_t)es * 8 + i];
+      const float zz[4] = {z.x, z.y, z.z, z.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float sg = bwd_sigmoid(zz[q]);
+        dz1[4 * i + q] = in ? ss[q] * (sg * (1.f + zz[q] * (1.f - sg))) * cst : 0.f;
+      }
+    }
+    // da1 = W1 dz1 / sqrt(32)
+    float2 da1[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) da1[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bwd_row_fma(dz1[j], sW1T + j * 32, da1);
+    __syncwarp();  // the previous chunk's tiles have been consumed
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(&T.dz1[lane * 32 + ((i ^ (lane & 7)) << 2)]) =
+          make_float4(dz1[4 * i], dz1[4 * i + 1], dz1[4 * i + 2], dz1[4 * i + 3]);
+    // a1, dz0 from z0; emb row
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 z = Z0[(size_t)es * 8 + i];
+      const float zz[4] = {z.x, z.y, z.z, z.w};
+      const float dd[4] = {da1[2 * i].x, da1[2 * i].y, da1[2 * i + 1].x, da1[2 * i + 1].y};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float sg = bwd_sigmoid(zz[q]);
+        T.a1[lane * 33 + 4 * i + q] = in ? zz[q] * sg * cst : 0.f;
+        T.dz0[lane * 33 + 4 * i + q] = in ? dd[q] * (sg * (1.f + zz[q] * (1.f - sg))) * cst : 0.f;
+      }
+    }
+    {
+      const float* er = emb + (size_t)p.perm[es] * in0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) T.emb[lane * 8 + k] = (in && k < in0) ? er[k] : 0.f;
+    }
+    __syncwarp();
+    // dW1[lane][:] += sum_e a1[e][lane] dz1[e][:]     dW0[:][lane] += sum_e emb[e][:] dz0[e][lane]
+#pragma unroll 4
+    for (int el = 0; el < 32; ++el) {
+      const float a = T.a1[el * 33 + lane];
+      const float* dr = &T.dz1[el * 32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 d = *reinterpret_cast<const float4*>(dr + ((i ^ (el & 7)) << 2));
+        fma_pair(a, d.x, d.y, gw1[2 * i]);
+        fma_pair(a, d.z, d.w, gw1[2 * i + 1]);
+      }
+      const float g0 = T.dz0[el * 33 + lane];
+      const float4 e0 = *reinterpret_cast<const float4*>(&T.emb[el * 8]);
+      const float4 e1 = *reinterpret_cast<const float4*>(&T.emb[el * 8 + 4]);
+      fma_pair(g0, e0.x, e0.y, gw0[0]);
+      fma_pair(g0, e0.z, e0.w, gw0[1]);
+      fma_pair(g0, e1.x, e1.y, gw0[2]);
+      fma_pair(g0, e1.z, e1.w, gw0[3]);
+    }
+  }
+  // this warp's partial: layer 0 at [k][j] = k * 32 + j (k < in0), layer 1 at in0 * 32 + i * 32 + j
+  float* part = static_cast<float*>(p.PARTH) + (size_t)wglobal * p.hid_numel;
+  const float g0v[8] = {gw0[0].x, gw0[0].y, gw0[1].x, gw0[1].y, gw0[2].x, gw0[2].y, gw0[3].x, gw0[3].y};
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < in0) part[k * 32 + lane] = g0v[k];
+  float4* p1 = reinterpret_cast<float4*>(part + in0 * 32 + lane * 32);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p1[i] = make_float4(gw1[2 * i].x, gw1[2 * i].y, gw1[2 * i + 1].x, gw1[2 * i + 1].y);
+}
+
 // ---------------------------------------------------------------------------------------------- K4
 template <typename T>
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const T* __restrict__ part, int64_t stride, int nparts,
