@@ -194,7 +194,7 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
     if (rc != MT_OK) return rc;
     {
       const int64_t cnt = (int64_t)H * Wn;
-      reduce_partials_kernel<T><<<(unsigned)ceil_div<int64_t>(cnt, 256), 256, 0, st>>>(
+      reduce_partials_kernel<T><<<(unsigned)ceil_div<int64_t>(cnt, 32), 256, 0, st>>>(
           static_cast<const T*>(p.PARTL), cnt, p.grid2, 0, cnt, T(1) / sqrt(T(H)), static_cast<T*>(grad_w[nl - 1]));
       MT_LAUNCH_OK();
     }
@@ -207,7 +207,7 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
       int64_t off = 0;
       for (int l = 0; l + 1 < nl; ++l) {
         const int64_t cnt = (int64_t)p.sizes[l] * p.sizes[l + 1];
-        reduce_partials_kernel<T><<<(unsigned)ceil_div<int64_t>(cnt, 256), 256, 0, st>>>(
+        reduce_partials_kernel<T><<<(unsigned)ceil_div<int64_t>(cnt, 32), 256, 0, st>>>(
             static_cast<const T*>(p.PARTH), p.hid_numel, nparts, off, cnt, T(1) / sqrt(T(p.sizes[l])),
             static_cast<T*>(grad_w[l]));
         MT_LAUNCH_OK();
@@ -226,7 +226,7 @@ static int conv_bwd_impl(const mt_conv_plan* plan, const void* x, const void* sh
       int64_t off = 0;
       for (int l = 0; l + 1 < nl; ++l) {
         const int64_t cnt = (int64_t)p.sizes[l] * p.sizes[l + 1];
-        reduce_partials_kernel<T><<<(unsigned)ceil_div<int64_t>(cnt, 256), 256, 0, st>>>(
+        reduce_partials_kernel<T><<<(unsigned)ceil_div<int64_t>(cnt, 32), 256, 0, st>>>(
             static_cast<const T*>(p.PARTH), p.hid_numel, p.grid3, off, cnt, T(1) / sqrt(T(p.sizes[l])),
             static_cast<T*>(grad_w[l]));
         MT_LAUNCH_OK();

@@ -659,15 +659,26 @@ __global__ void __launch_bounds__(32 * kHidFastWarps) mlp_bwd_hidden_fast_kernel
 }
 
 // ---------------------------------------------------------------------------------------------- K4
+// CTA <-> 32 outputs x 8 partial groups: thread (o, g) sums partials g, g + 8, ... in order, the 8 group sums are then
+// added in order -- a fixed summation tree (deterministic) with 8 x the memory parallelism of one serial loop per output.
 template <typename T>
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const T* __restrict__ part, int64_t stride, int nparts,
                                                               int64_t off, int64_t count, T scale,
                                                               T* __restrict__ out) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= count) return;
+  __shared__ T sh[8][33];
+  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t i = blockIdx.x * 32ll + o;
   T s = T(0);
-  for (int b = 0; b < nparts; ++b) s += part[(size_t)b * stride + off + i];
-  out[i] = s * scale;
+  if (i < count)
+    for (int b = g; b < nparts; b += 8) s += part[(size_t)b * stride + off + i];
+  sh[g][o] = s;
+  __syncthreads();
+  if (g == 0 && i < count) {
+    T t = sh[0][o];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sh[k][o];
+    out[i] = t * scale;
+  }
 }
 
 }  // namespace mt
