@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(256) tc_ypairs_kernel(const float* __restrict_
 // 32 hidden outputs of the column in registers, weights by warp-wide broadcast LDS.128.  Per input channel a lane
 // issues 8 LDS.128 and 16 FFMA2 and nothing else (the generic kernel above spends 40 % of its instructions on
 // predicates, index arithmetic and the shared-memory exchange between its four lanes per column: ncu r2_step_full).
-__global__ void __launch_bounds__(256) tc_edge_hidden_fast_kernel(const ConvTcParams p) {
+__global__ void __launch_bounds__(256, 3) tc_edge_hidden_fast_kernel(const ConvTcParams p) {
   __shared__ __align__(16) float sW0[8 * kTcK];
   __shared__ __align__(16) float sW1[kTcK * kTcK];
   const int in0 = p.sizes[0];

@@ -132,10 +132,32 @@ def get_pretrained_config(identifier: str, config_filename: str = "config_final.
         return yaml.safe_load(f)
 
 
+_MODEL_CACHE: Dict[Any, Any] = {}
+
+
 def get_pretrained_model(identifier: str, checkpoint: str = "model_final.ckpt", model_class=ScalarTensorModel,
                          device=None):
     """``model_class.load_from_checkpoint`` of the reference: hyper-parameters and weights from the checkpoint (the
-    backbone section of ``config_final.yaml`` is the fallback when the checkpoint carries no hyper-parameters)."""
+    backbone section of ``config_final.yaml`` is the fallback when the checkpoint carries no hyper-parameters).
+    The loaded model (weights on the device, kernel plans built) is kept for the next call as long as the checkpoint
+    file is unchanged: repeated ``predict()`` calls then cost the forward only."""
+    directory = get_pretrained_model_dir(identifier)
+    ck_path = directory / checkpoint
+    try:
+        st = os.stat(ck_path)
+        key = (str(ck_path.resolve()), st.st_mtime_ns, st.st_size, model_class.__name__, str(device))
+    except OSError:
+        key = None
+    if key is not None and key in _MODEL_CACHE:
+        return _MODEL_CACHE[key]
+    model = _load_pretrained_model(identifier, checkpoint, model_class, device)
+    if key is not None:
+        _MODEL_CACHE.clear()  # one model at a time: checkpoints are large
+        _MODEL_CACHE[key] = model
+    return model
+
+
+def _load_pretrained_model(identifier: str, checkpoint: str, model_class, device):
     directory = get_pretrained_model_dir(identifier)
     ck = load_checkpoint(directory / checkpoint)
     hp = ck.get("hyper_parameters") or {}
