@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-] + (["-DMT_TC_TIMING"] if os.environ.get("MT_TC_TIMING") else [])  # phase timing of the tcgen05 conv (tools/tc_debug.py)
+] + (["-DMT_TC_TIMING"] if os.environ.get("MT_TC_TIMING") else [])  # legacy switch (round 1); phase timing is now run time: TC_TIMING=1 tools/tc_check.py
 
 PLAIN_SOURCES = ["api.cu", "graph_ops.cu", "node_ops.cu", "train_ops.cu", "norm_ops.cu", "conv.cu", "conv_fwd_tc.cu", "conv_bwd.cu"]
 CONV_INST = [(t, hp) for t in ("float", "double") for hp in (8, 16, 32, 64)]
