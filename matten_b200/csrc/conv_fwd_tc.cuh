@@ -10,22 +10,26 @@
 // Same contract as conv_fwd.cuh (reference src/matten/nn/utils.py:260-263 + src/matten/nn/conv.py:113-120): the
 // per-edge tensor-product weights [E, weight_numel] and the messages [E, D_mid] never leave the SM.
 //
-// Three kernels per call:
-//  (1) tc_pad_layout_kernel: the receiver-sorted edge list in PADDED column order -- every node's edges padded to a
-//      multiple of 4 columns (pad columns repeat the node's last edge and get zero weights): per column the original
-//      edge id and the sender row.  With this layout every chunk of the fused kernel is ONE contiguous column range.
-//  (2) tc_edge_hidden_kernel: the small hidden layers of the radial MLP (8 -> 32 -> 32) per column, four lanes per
-//      column, written as three bf16 planes (hi / mid / lo) in the K-major core-matrix layout the MMA wants (192 bytes
-//      per column), plus the edge's spherical harmonics as pair-interleaved padded rows.
+// Kernels:
+//  (0) once per batch (mt_conv_layout_prepare; or at every call when the caller passes no layout):
+//      tc_pad_degree / scan / tc_pad_layout_kernel: the receiver-sorted edge list in PADDED column order -- every
+//      node's edges padded to a multiple of 4 columns (pad columns repeat the node's last edge and get zero weights):
+//      per column the original edge id and the sender row.  With this layout every chunk of the fused kernel is ONE
+//      contiguous column range.  tc_ypairs_kernel: the edges' spherical harmonics as pair-interleaved padded rows.
+//  (1) tc_edge_hidden_fast_kernel (MLP shape <= 8 -> 32 -> 32, silu; tc_edge_hidden_kernel otherwise): the small
+//      hidden layers of the radial MLP per column, written as three bf16 planes (hi / mid / lo) in the K-major
+//      core-matrix layout the MMA wants (192 bytes per column).
 //      (Round 2 also built this stage INTO the fused kernel, on dedicated warps: correct, but slower -- a lone warp
 //      per scheduler runs such code at ~10 cycles per instruction and the h planes of the next chunk sat on the
 //      critical path; measurements in DESIGN.md.)
-//  (3) conv_fwd_tc_kernel: 1 CTA per SM, persistent over a contiguous node range (balanced by edge count), 18 warps:
-//        warp 0      builds node-aligned chunks (<= NE columns) and issues the copies of the chunk: 12 bulk copies of
-//                    the h planes, one of the sh rows, one TMA gather of 4 sender rows per 4 columns;
+//  (2) conv_fwd_tc_kernel: 1 CTA per SM, persistent over a contiguous node range (balanced by edge count), 20 warps:
+//        warp 0      builds node-aligned chunks (<= NE columns) and issues the copies of the chunk: one 3D TMA tile
+//                    load of the twelve h-plane segments and one bulk copy of the sh pair rows;
 //        warp 1      one thread issues the tcgen05.mma's of the chunk: D[t] (128 x NE, TMEM) = A[t] (128 rows of W^T,
 //                    K = 32) x B^T (NE columns), 6 significant products of the 3 x 3 bf16 split (~2^-24);
-//        warps 2..17 consumers.  Warp w reads TMEM lanes 32 (w % 4) .. .  Work units (bundle instance, node) are
+//        warp 2      TMA gathers of the sender rows, 4 rows per instruction (warp 3 takes the odd groups for one-tile
+//                    parts, whose chunks are 256 columns; it idles otherwise);
+//        warps 4..19 consumers.  Warp w reads TMEM lanes 32 (w % 4) .. .  Work units (bundle instance, node) are
 //                    handed out dynamically per quarter.  A bundle instance (matten_b200/tcplan.py) is a group of
 //                    input channels x a compile-time list of paths that share the loads of x[u, :] and Y
 //                    (generated/cg_bundles.cuh):
@@ -33,7 +37,7 @@
 //                      mode P: 8 / 4 / 2 channels x edge phases through the tcgen05.ld.16x256b fragment
 //                              (thread 4 r + ph: TMEM rows r and r + 8, column pair ph of 4).
 //      Double buffered TMEM accumulators and x / Y staging; mbarriers: full[b] (copy bytes + tcgen05.commit),
-//      empty[b] (consumers), bready / bfree (h planes landed / consumed by the MMAs).
+//      empty[b] (consumers), go[b] (gather warps), bready / bfree (h planes landed / consumed by the MMAs).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
