@@ -63,8 +63,9 @@ def main():
             _lib.load().mt_conv_set_debug_buffer(None)
             ops.conv_select_impl("auto")
             t = dbg.cpu().reshape(32, 8)
-            for w in range(19):
-                role = "prod[layout,wait_empty,wait_bfree,copies]" if w == 0 else "mma[wait_bready,issue]" if w == 1 else "gather[wait_go,issue]" if w == 2 else "cons[wait_full,units,..,n_units]"
+            for w in range(20):
+                role = ("prod[layout,wait_empty,wait_bfree,copies]" if w == 0 else "mma[wait_bready,issue]" if w == 1
+                        else "gather[wait_go,issue]" if w in (2, 3) else "cons[wait_full,units,..,n_units]")
                 print(f"   warp {w:2d} {role}: " + " ".join(f"{int(v) / 1e3:.0f}k" if i < 7 else str(int(v)) for i, v in enumerate(t[w].tolist())), flush=True)
         a, b = outs["tc"].double(), outs["fma"].double()
         res["max_abs_diff"] = float((a - b).abs().max())
